@@ -1,0 +1,454 @@
+// Column-sparse "delta" attention and dense attention (+ column sums) for sm_100a.
+//
+// Replaces csrc/attn/{csp_attn,csp_128_attn,dense_attn,dense_colsum_attn}.cu of the reference
+// (Hopper wgmma + ThunderKittens) with one warp-specialised tcgen05 kernel template.
+//
+// Work unit ("tile"): one (batch, head, group of 192 query rows).  Per tile the kernel walks the
+// group's selected key columns 128 at a time:
+//     producers (4 warps)  gather K[idx] / V[idx] rows (256 B each) with 16-byte cp.async into
+//                          128B-swizzled shared-memory slots (a 5-deep ring of 32 KB slots),
+//     MMA warp (1 thread)  S = Q K^T   (tcgen05.mma SS, M=128 N<=128 K=128, fp32 in TMEM), twice:
+//                          query rows 0-127 ("block 0") and 128-191 ("block 1"),
+//                          O += P V    (tcgen05.mma TS: P read from TMEM, V as MN-major smem),
+//     softmax warps (4+2)  one thread per query row: TMEM -> regs, running max with lazy
+//                          rescale, exp2, row sum, P (bf16) written back over S in TMEM,
+//     epilogue             (same threads) O / l * o_scale -> bf16, optional add of the cached
+//                          output tile, store.  Dense mode also writes l and the column sums.
+// The two query blocks ping-pong on the tensor pipe: while the softmax warps of block 0 work on
+// S0(k), the pipe runs S1(k) / P1 V(k-1), and vice versa.
+//
+// TMEM map (512 columns): S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512);  P aliases the
+// first 64 columns of its S.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/chipmunk_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cm {
+namespace attn {
+
+constexpr int D = 128;              // head dim
+constexpr int QG = 192;             // query rows per tile
+constexpr int KT = 128;             // key columns per step
+constexpr int NSLOT = 5;            // 32 KB K/V slots
+constexpr int SLOT_BYTES = KT * D * 2;
+constexpr int Q_HALF_BYTES = QG * 128;          // one 64-wide d-half of the Q tile
+constexpr int Q_BYTES = 2 * Q_HALF_BYTES;       // 49152
+constexpr int SMEM_BYTES = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
+
+constexpr int NUM_THREADS = 384;    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
+constexpr int WARP_MMA = 6;
+constexpr int WARP_PROD0 = 8;
+constexpr int NUM_PROD = 128;
+
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 384;
+
+constexpr float SCALE_LOG2 = 0.08838834764f * 1.44269504089f;   // log2(e)/sqrt(128)
+constexpr float RESCALE_THRESHOLD = 8.0f;                        // in log2 units
+
+struct Params {
+    const __nv_bfloat16* q;
+    const __nv_bfloat16* k;
+    const __nv_bfloat16* v;
+    __nv_bfloat16* o;
+    const int32_t* indices;      // null in dense mode
+    const int32_t* counts;       // null in dense mode
+    float* l;                    // dense mode: [B,H,Nq]
+    int B, H, Nq, Nk, G;
+    int64_t qs[3], ks[3], vs[3], os[3];
+    int64_t idx_row_stride;
+    float o_scale;
+    int accumulate;
+    int num_tiles;
+};
+
+struct __align__(8) Barriers {
+    uint64_t q_full, q_empty;
+    uint64_t kv_full[NSLOT], kv_empty[NSLOT];
+    uint64_t s_full[2], p_full[2], o_full[2];
+};
+
+__device__ __forceinline__ int tile_count(const Params& P, int tile, bool dense) {
+    if (dense) return P.Nk;
+    int c = __ldg(P.counts + tile);
+    c = c < 0 ? 0 : c;
+    return c > (int)P.idx_row_stride ? (int)P.idx_row_stride : c;
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool DENSE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = sbase;
+    const uint32_t sKV = sbase + Q_BYTES;
+
+    if (tid == 0) {
+        mbar_init(&bar.q_full, NUM_PROD);
+        mbar_init(&bar.q_empty, 1);
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&bar.kv_full[i], NUM_PROD); mbar_init(&bar.kv_empty[i], 1); }
+        mbar_init(&bar.s_full[0], 1);  mbar_init(&bar.s_full[1], 1);
+        mbar_init(&bar.p_full[0], 128); mbar_init(&bar.p_full[1], 64);
+        mbar_init(&bar.o_full[0], 1);  mbar_init(&bar.o_full[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == WARP_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = tmem_base_s;
+
+    // =========================================================================== producers
+    if (warp >= WARP_PROD0) {
+        const int pt = tid - WARP_PROD0 * 32;       // 0..127
+        const int chunk = pt & 15;                  // 16-byte chunk of the 256-byte row
+        const int rsub = pt >> 4;                   // 0..7
+        const uint32_t half_off = (uint32_t)(chunk >> 3);
+        const uint32_t c8 = (uint32_t)(chunk & 7);
+        uint32_t job = 0;                           // K/V slot fills issued so far
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
+            const int count = tile_count(P, tile, DENSE);
+            if (count <= 0) { it--; continue; }
+            const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
+            // ---- Q tile (192 rows, zero-filled past Nq)
+            mbar_wait(&bar.q_empty, (it & 1) ^ 1);
+            {
+                const __nv_bfloat16* qb = P.q + b * P.qs[0] + h * P.qs[1];
+#pragma unroll 4
+                for (int i = 0; i < QG / 8; i++) {
+                    const int r = rsub + 8 * i;
+                    const int row = g * QG + r;
+                    const bool ok = row < P.Nq;
+                    const __nv_bfloat16* src = qb + (ok ? row : 0) * P.qs[2] + chunk * 8;
+                    cp_async_16_zfill(sQ + half_off * Q_HALF_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+                }
+                cp_async_mbar_arrive_noinc(&bar.q_full);
+            }
+            const __nv_bfloat16* kb = P.k + b * P.ks[0] + h * P.ks[1];
+            const __nv_bfloat16* vb = P.v + b * P.vs[0] + h * P.vs[1];
+            const int32_t* ip = DENSE ? nullptr : P.indices + (int64_t)tile * P.idx_row_stride;
+            const int nk = (count + KT - 1) / KT;
+            for (int kk = 0; kk < nk; kk++) {
+                int64_t off[KT / 8];
+                uint32_t okm = 0;
+#pragma unroll
+                for (int i = 0; i < KT / 8; i++) {
+                    const int pos = kk * KT + rsub + 8 * i;
+                    const bool ok = pos < count;
+                    int idx = DENSE ? pos : (ok ? __ldg(ip + pos) : 0);
+                    idx = idx < 0 ? 0 : (idx >= P.Nk ? P.Nk - 1 : idx);
+                    off[i] = ok ? (int64_t)idx : -1;
+                    okm |= (ok ? 1u : 0u) << i;
+                }
+#pragma unroll
+                for (int op = 0; op < 2; op++) {
+                    const uint32_t slot = job % NSLOT;
+                    mbar_wait(&bar.kv_empty[slot], ((job / NSLOT) & 1) ^ 1);
+                    const uint32_t dst0 = sKV + slot * SLOT_BYTES + half_off * (SLOT_BYTES / 2);
+                    const __nv_bfloat16* base = op == 0 ? kb : vb;
+                    const int64_t rs = op == 0 ? P.ks[2] : P.vs[2];
+#pragma unroll
+                    for (int i = 0; i < KT / 8; i++) {
+                        const int r = rsub + 8 * i;
+                        const bool ok = (okm >> i) & 1u;
+                        const __nv_bfloat16* src = base + (ok ? off[i] : 0) * rs + chunk * 8;
+                        cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+                    }
+                    cp_async_mbar_arrive_noinc(&bar.kv_full[slot]);
+                    job++;
+                }
+            }
+        }
+        cp_async_wait_all();
+    }
+    // =========================================================================== MMA issuer
+    else if (warp == WARP_MMA) {
+        uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
+        const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
+            const int count = tile_count(P, tile, DENSE);
+            if (count <= 0) { it--; continue; }
+            const int nk = (count + KT - 1) / KT;
+            auto ncols = [&](int kk) { int v = count - kk * KT; v = v > KT ? KT : v; return (v + 15) & ~15; };
+
+            auto issue_S = [&](int blk, uint32_t slot, int cols) {
+                const uint32_t idesc = umma_idesc_bf16(128, cols, 0, 0);
+                const uint32_t d = tm + (blk ? TM_S1 : TM_S0);
+#pragma unroll
+                for (int k16 = 0; k16 < D / 16; k16++) {
+                    uint64_t ad = umma_smem_desc(sQ + (k16 >> 2) * Q_HALF_BYTES + blk * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+                    uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + (k16 >> 2) * (SLOT_BYTES / 2) + (k16 & 3) * 32, 16, 1024);
+                    umma_ss(d, ad, bd, idesc, k16 > 0);
+                }
+            };
+            auto issue_PV = [&](int blk, uint32_t slot, int cols, bool first) {
+                const uint32_t d = tm + (blk ? TM_O1 : TM_O0);
+                const uint32_t a = tm + (blk ? TM_S1 : TM_S0);
+                for (int j = 0; j < cols / 16; j++) {
+                    uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + j * 2048, SLOT_BYTES / 2, 1024);
+                    umma_ts(d, a + j * 8, bd, idesc_pv, (!first) || j > 0);
+                }
+            };
+
+            mbar_wait(&bar.q_full, it & 1);
+            // prologue: S0(0), S1(0)
+            uint32_t slotK = job % NSLOT;
+            mbar_wait(&bar.kv_full[slotK], (job / NSLOT) & 1);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                issue_S(0, slotK, ncols(0)); umma_commit(&bar.s_full[0]);
+                issue_S(1, slotK, ncols(0)); umma_commit(&bar.s_full[1]);
+                umma_commit(&bar.kv_empty[slotK]);
+                if (nk == 1) umma_commit(&bar.q_empty);
+            }
+            __syncwarp();
+            job++;
+            for (int kk = 0; kk < nk; kk++) {
+                const uint32_t slotV = job % NSLOT;
+                mbar_wait(&bar.kv_full[slotV], (job / NSLOT) & 1);
+                job++;
+                const bool more = kk + 1 < nk;
+                uint32_t slotKn = 0;
+                if (more) {
+                    slotKn = job % NSLOT;
+                    mbar_wait(&bar.kv_full[slotKn], (job / NSLOT) & 1);
+                    job++;
+                }
+                // block 0
+                mbar_wait(&bar.p_full[0], sc0 & 1); sc0++;
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    issue_PV(0, slotV, ncols(kk), kk == 0);
+                    if (more) { issue_S(0, slotKn, ncols(kk + 1)); umma_commit(&bar.s_full[0]); }
+                    else umma_commit(&bar.o_full[0]);
+                }
+                __syncwarp();
+                // block 1
+                mbar_wait(&bar.p_full[1], sc1 & 1); sc1++;
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    issue_PV(1, slotV, ncols(kk), kk == 0);
+                    umma_commit(&bar.kv_empty[slotV]);
+                    if (more) {
+                        issue_S(1, slotKn, ncols(kk + 1)); umma_commit(&bar.s_full[1]);
+                        umma_commit(&bar.kv_empty[slotKn]);
+                        if (kk + 2 == nk) umma_commit(&bar.q_empty);
+                    } else umma_commit(&bar.o_full[1]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // =========================================================================== softmax + epilogue
+    else if (warp < 6) {
+        const int blk = warp >> 2;                         // 0: rows 0-127, 1: rows 128-191
+        const int r_in_tile = blk * 128 + (warp & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tm + (blk ? TM_S1 : TM_S0) + lane_off;
+        const uint32_t tO = tm + (blk ? TM_O1 : TM_O0) + lane_off;
+        uint32_t sc = 0, oc = 0;
+
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            const int count = tile_count(P, tile, DENSE);
+            const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
+            const int row = g * QG + r_in_tile;
+            const bool row_ok = row < P.Nq;
+            __nv_bfloat16* orow = P.o + b * P.os[0] + h * P.os[1] + (int64_t)(row_ok ? row : 0) * P.os[2];
+            if (count <= 0) {
+                if (!P.accumulate && row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            const int nk = (count + KT - 1) / KT;
+            float m_ref = -INFINITY;       // reference max, raw score units
+            float l_sum = 0.f;
+
+            for (int kk = 0; kk < nk; kk++) {
+                const int valid = min(KT, count - kk * KT);
+                const int cols = (valid + 15) & ~15;
+                mbar_wait(&bar.s_full[blk], sc & 1); sc++;
+                tc_fence_after_sync();
+                // ---- pass 1: tile max
+                float m_tile = -INFINITY;
+                for (int c0 = 0; c0 < cols; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float s = __uint_as_float(r[j]);
+                        m_tile = (c0 + j < valid) ? fmaxf(m_tile, s) : m_tile;
+                    }
+                }
+                // ---- lazy rescale of the running state
+                const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;   // true on the first step
+                if (__any_sync(0xffffffffu, need)) {
+                    float alpha = 1.f;
+                    if (need) {
+                        alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);   // exp2(-inf) = 0 on the first step
+                        m_ref = m_tile;
+                        l_sum *= alpha;
+                    }
+                    if (kk > 0) {
+                        for (int c0 = 0; c0 < D; c0 += 32) {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(tO + c0, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+                            tmem_st_32x32b_x32(tO + c0, r);
+                        }
+                    }
+                }
+                const float neg_m = -m_ref * SCALE_LOG2;
+                // ---- pass 2: P = exp2(s*c - m*c), row sum, bf16 pack, write over S
+                for (int c0 = 0; c0 < cols; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + c0, r);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, neg_m));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, neg_m));
+                        p0 = (c0 + j < valid) ? p0 : 0.f;
+                        p1 = (c0 + j + 1 < valid) ? p1 : 0.f;
+                        l_sum += p0 + p1;
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st_32x32b_x16(tS + (c0 >> 1), pk);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                mbar_arrive(&bar.p_full[blk]);
+            }
+            // ---- epilogue: O / l * scale (+ cached o) -> bf16
+            mbar_wait(&bar.o_full[blk], oc & 1); oc++;
+            tc_fence_after_sync();
+            const float inv = P.o_scale / l_sum;
+            if (DENSE && row_ok && P.l) P.l[(int64_t)bh * P.Nq + row] = 1.f / (fast_exp2(m_ref * SCALE_LOG2) * l_sum);
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tO + c0, r);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            w[j] = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]) * inv, __uint_as_float(r[q4 * 8 + 2 * j + 1]) * inv);
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c0 + q4 * 8);
+                        if (P.accumulate) {
+                            uint4 old = *dst;
+                            uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                w[j] = pack_bf16x2(bf16_lo(ov[j]) + bf16_lo(w[j]), bf16_hi(ov[j]) + bf16_hi(w[j]));
+                        }
+                        *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            tc_fence_before_sync();
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tm, 512);
+}
+
+}  // namespace attn
+}  // namespace cm
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+using namespace cm;
+using namespace cm::attn;
+
+template <bool DENSE>
+static int launch_attn(Params& P, cudaStream_t stream) {
+    static bool configured = false;
+    auto kern = attn_kernel<DENSE>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool strides_ok(const int64_t s[3]) { return s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0; }
+
+extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,
+                           const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
+                           const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
+                           int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
+    if (B < 0 || H < 0 || Nq < 0 || Nk <= 0 || idx_row_stride <= 0) return CM_EINVAL;
+    if (o_scale != 1 && o_scale != -1) return CM_EINVAL;
+    if ((int64_t)B * H * Nq == 0) return CM_OK;
+    if (!q || !k || !v || !o || !indices || !counts) return CM_EINVAL;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return CM_EALIGN;
+    if (!strides_ok(q_strides) || !strides_ok(k_strides) || !strides_ok(v_strides) || !strides_ok(o_strides))
+        return CM_EALIGN;
+    if (!is_sm100()) return CM_EARCH;
+    Params P{};
+    P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
+    P.o = (__nv_bfloat16*)o;
+    P.indices = indices; P.counts = counts; P.l = nullptr;
+    P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
+    for (int i = 0; i < 3; i++) { P.qs[i] = q_strides[i]; P.ks[i] = k_strides[i]; P.vs[i] = v_strides[i]; P.os[i] = o_strides[i]; }
+    P.idx_row_stride = idx_row_stride;
+    P.o_scale = (float)o_scale;
+    P.accumulate = accumulate ? 1 : 0;
+    int64_t tiles = (int64_t)B * H * P.G;
+    if (tiles > 2147483647ll) return CM_EINVAL;
+    P.num_tiles = (int)tiles;
+    return launch_attn<false>(P, (cudaStream_t)stream);
+}
+
+namespace cm { namespace attn {
+int launch_colsum(const __nv_bfloat16* q, const __nv_bfloat16* k, const float* p, __nv_bfloat16* cs, int B, int H,
+                  int Nq, int Nk, int64_t cs_row_stride, cudaStream_t stream);
+} }
+
+extern "C" int cm_dense_attn(const void* q, const void* k, const void* v, void* o, float* l, void* cs,
+                             const float* p, int B, int H, int Nq, int Nk, int64_t cs_row_stride, void* stream) {
+    if (B < 0 || H < 0 || Nq < 0 || Nk <= 0) return CM_EINVAL;
+    if ((int64_t)B * H * Nq == 0) return CM_OK;
+    if (!q || !k || !v || !o) return CM_EINVAL;
+    if (cs && (!p || cs_row_stride < Nk)) return CM_EINVAL;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return CM_EALIGN;
+    if (!is_sm100()) return CM_EARCH;
+    Params P{};
+    P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
+    P.o = (__nv_bfloat16*)o;
+    P.indices = nullptr; P.counts = nullptr; P.l = l;
+    P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
+    const int64_t qst[3] = {(int64_t)H * Nq * D, (int64_t)Nq * D, D};
+    const int64_t kst[3] = {(int64_t)H * Nk * D, (int64_t)Nk * D, D};
+    for (int i = 0; i < 3; i++) { P.qs[i] = qst[i]; P.os[i] = qst[i]; P.ks[i] = kst[i]; P.vs[i] = kst[i]; }
+    P.idx_row_stride = Nk;
+    P.o_scale = 1.f;
+    P.accumulate = 0;
+    int64_t tiles = (int64_t)B * H * P.G;
+    if (tiles > 2147483647ll) return CM_EINVAL;
+    P.num_tiles = (int)tiles;
+    int rc = launch_attn<true>(P, (cudaStream_t)stream);
+    if (rc != 0 || !cs) return rc;
+    return launch_colsum(P.q, P.k, p, (__nv_bfloat16*)cs, B, H, Nq, Nk, cs_row_stride, (cudaStream_t)stream);
+}

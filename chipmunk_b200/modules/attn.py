@@ -1,0 +1,157 @@
+"""SparseDiffAttn: dense attention on "full" steps, column-sparse delta attention on the rest.
+
+Behavioural mirror of src/chipmunk/modules/attn.py:16-200 (same constructor, same config keys,
+same cache algebra: the cache holds dense(q,k,v) - sparse(q,k,v) of the last full step and a
+sparse step returns cache + sparse(q,k,v)).  Differences, all on the B200 side of the boundary:
+  * sparse steps with compressed indices turn the stored bit mask into indices with ONE fused
+    kernel (bitmask_to_indices) instead of bitunpack + mask_to_indices;
+  * no padding copies: the kernels take any sequence length and strided q/k/v;
+  * the delta add-back is always fused into the attention epilogue (csp_attn with o_scale=+-1),
+    also on the `pad_qkv_before_kernel` path.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor, nn
+from torch.nn import functional as F
+
+from .. import ops
+from ..util import GLOBAL_CONFIG, AttnStorage, LayerCounter
+
+# shared by all layers, set by initialize_static_mask (video models only)
+singleton_static_mask = None
+singleton_video_query_groups = None
+
+
+class SparseDiffAttn(nn.Module):
+    def __init__(self, layer_num: int, layer_counter: LayerCounter):
+        super().__init__()
+        self.layer_num = layer_num
+        self.layer_counter = layer_counter
+        self.storage = AttnStorage(layer_num, init_names=["indices", "out_cache"])
+        self.mask_shape = [None] * GLOBAL_CONFIG["num_model_invocations_per_inference_step"]
+
+    # ------------------------------------------------------------------ static (local) mask
+    def initialize_static_mask(self, seq_shape: Tuple, txt_len: int, local_heads_num: int, device):
+        """3-D local-voxel window (+ optional 1-D window) that is always attended to
+        (reference modules/attn.py:23-73)."""
+        if len(seq_shape) == 2:
+            raise NotImplementedError("Not yet implemented for 2D sequences")
+        from ..ops.voxel import get_local_indices_with_text
+
+        tt, th, tw = seq_shape
+        cfg = GLOBAL_CONFIG["attn"]
+        n_vid = tt * th * tw
+        topk = int(cfg["top_keys"] * n_vid)
+        lv = cfg["local_voxels"]
+        mask, _, _ = get_local_indices_with_text(vid_shape=(tt, th, tw), txt_len=txt_len, voxel_shape=(4, 6, 8),
+                                                 local_shape=(lv, lv, lv), rk=cfg["random_keys"], device=device)
+        if cfg["local_1d_window"] > 0:
+            half = int(cfg["local_1d_window"] * n_vid) // 2
+            groups = n_vid // 192
+            centers = torch.arange(groups, device=device) * 192 + 96
+            cols = torch.arange(mask.shape[-1], device=device)
+            lo = (centers - half).clamp_(min=0)[:, None]
+            hi = (centers + half).clamp_(max=n_vid)[:, None]
+            mask[:groups] |= (cols[None, :] >= lo) & (cols[None, :] < hi)
+        mask = mask[None, None].expand(1, local_heads_num, -1, -1).contiguous()
+        sparse_groups = (mask.sum(dim=-1, keepdim=True) + topk) < (n_vid + txt_len)
+
+        global singleton_static_mask, singleton_video_query_groups
+        singleton_static_mask = mask
+        singleton_video_query_groups = sparse_groups
+
+    def random_and_topk(self, cs: Tensor, topk: int) -> Tensor:
+        """1 % random columns + top-k column sums (+ static mask) -> bool mask [B,H,G,N]
+        (reference modules/attn.py:76-84)."""
+        mask = torch.randint(0, 100, cs.shape, device=cs.device, dtype=torch.uint8) == 0
+        mask.scatter_(-1, cs.topk(k=topk, dim=-1).indices, True)
+        if singleton_static_mask is not None:
+            qg, n = cs.shape[-2], cs.shape[-1]
+            mask = (mask * singleton_video_query_groups[..., :qg, :n]) | singleton_static_mask[..., :qg, :n]
+        return mask
+
+    # ------------------------------------------------------------------ index bookkeeping
+    def _stored_indices(self, multiple_of: int, bm: int):
+        cfg = GLOBAL_CONFIG["attn"]
+        if cfg["should_compress_indices"]:
+            shape = self.mask_shape[self.layer_counter.cur_model_invocation_per_step]
+            return ops.bitmask_to_indices(self.storage.get_indices(), shape, multiple_of, bm)
+        return self.storage.get_indices(), self.storage.get_counts()
+
+    def _select_indices(self, cs: Tensor, q: Tensor, k: Tensor, multiple_of: int, bm: int):
+        cfg = GLOBAL_CONFIG["attn"]
+        kseq = k.shape[-2]
+        tk = int(multiple_of * round((cfg["top_keys"] * kseq) / multiple_of))
+        if cfg["should_compress_indices"]:
+            if tk > 0:
+                mask = self.random_and_topk(cs, tk)
+            else:
+                mask = singleton_static_mask[..., : cs.shape[-2], : cs.shape[-1]]
+            packed, shape = ops.bitpack(mask)
+            self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
+            self.storage.set_indices(packed)
+            return ops.mask_to_indices(mask, multiple_of, bm)
+        groups = (q.shape[-2] + bm - 1) // bm
+        cs = cs[..., : (kseq + bm - 1) // bm, :kseq]
+        top = torch.topk(cs, k=tk, dim=-1).indices.to(torch.int32)
+        inds = torch.empty((*top.shape[:-1], q.shape[-2]), device=q.device, dtype=torch.int32)
+        inds[..., :tk] = top
+        counts = torch.full((q.shape[0], q.shape[1], groups), tk, device=q.device, dtype=torch.int32)
+        self.storage.set_indices(inds)
+        self.storage.set_counts(counts)
+        return inds, counts
+
+    # ------------------------------------------------------------------ the step
+    def _fast_attention(self, q: Tensor, k: Tensor, v: Tensor, inference_step: int, do_full_step: bool) -> Tensor:
+        cfg = GLOBAL_CONFIG["attn"]
+        bm = cfg["mbm"]
+        assert bm == 192, "The kernels are written for 192-query groups"
+        multiple_of = 128 if cfg["pad_qkv_before_kernel"] else cfg["counts_multiple_of"]
+
+        if self.layer_num < cfg["first_n_dense_layers"]:
+            return ops.dense_attn(q, k, v)[0]
+
+        if do_full_step:
+            inds = counts = None
+            if inference_step == 0:
+                o, lse = ops.dense_attn(q, k, v)
+                lse[..., k.shape[-2]:, :] = 0
+                self.storage.set_lse_constants(lse)
+                return o
+            if inference_step == 1 or cfg["recompute_mask"]:
+                o, cs, lse = ops.dense_colsum_attn(q, k, v, self.storage.get_lse_constants())
+                lse[..., k.shape[-2]:, :] = 0
+                self.storage.set_lse_constants(lse)
+                inds, counts = self._select_indices(cs, q, k, multiple_of, bm)
+            else:
+                o = ops.dense_attn(q, k, v)[0]
+            if not cfg["recompute_mask"] or inds is None:
+                inds, counts = self._stored_indices(multiple_of, bm)
+            # cache = dense - sparse, with the subtraction done by the kernel epilogue
+            o_cache = o.clone()
+            torch.ops.chipmunk.csp_attn(q, k, v, o_cache, inds, counts, -1)
+            self.storage.set_out_cache(o_cache)
+            return o
+
+        # sparse step: out = cache + sparse(q, k, v), accumulated in the kernel epilogue
+        inds, counts = self._stored_indices(multiple_of, bm)
+        o = self.storage.get_out_cache()
+        if not self.storage.out_cache.is_offload_enabled:
+            o = o.clone()          # the cache must survive; offloaded caches are reloaded anyway
+        torch.ops.chipmunk.csp_attn(q, k, v, o, inds, counts, 1)
+        return o
+
+    def forward(self, q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+        if not GLOBAL_CONFIG["attn"]["is_enabled"]:
+            return F.scaled_dot_product_attention(q, k, v)
+        do_full_step = self.layer_counter.should_do_full_attn_step()
+        step = self.layer_counter.cur_inference_step
+        out = self._fast_attention(q, k, v, step, do_full_step)
+        self.layer_counter.increment()
+        return out
+
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)

@@ -1,0 +1,218 @@
+"""Per-layer cache slots for the sparse-delta modules.
+
+Public surface mirrors src/chipmunk/util/storage/{layer_storage,offloaded_tensor}.py
+(`AttnStorage`, `MlpStorage`, `LayerStorage`, `MaybeOffloadedTensor`, `PIPELINE_DEPTH`, and the
+`load_async / load_async_wait / complete_cur_layer` calls the model loops make), but the
+default residency is different: on B200 every cache stays in HBM (see util/config.py).  Host
+offload remains available behind the same config keys; it uses right-sized pinned buffers that
+grow on demand (the reference pre-allocates up to 1.2 GB per tensor name) and two lazily
+created copy streams, so importing this module never touches CUDA.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .config import GLOBAL_CONFIG
+
+# GPU slots kept alive per tensor name while offloading (layer L uses slot L % PIPELINE_DEPTH)
+PIPELINE_DEPTH = 2
+
+_streams: Dict[str, "torch.cuda.Stream"] = {}
+_gpu_slots: Dict[str, List[Optional[torch.Tensor]]] = {}
+
+
+def _stream(kind: str) -> "torch.cuda.Stream":
+    if kind not in _streams:
+        _streams[kind] = torch.cuda.Stream()
+    return _streams[kind]
+
+
+def _invocations() -> int:
+    return GLOBAL_CONFIG["num_model_invocations_per_inference_step"]
+
+
+class MaybeOffloadedTensor:
+    """One named cache of one layer.  Resident mode: a list of GPU tensors, one per model
+    invocation of a step (cond / uncond).  Offload mode: pinned host copies plus a
+    PIPELINE_DEPTH-deep ring of GPU staging tensors shared by all layers of the same name."""
+
+    # kept for callers that pass cpu_buf_size (sizes in bytes, reference offloaded_tensor.py:42-44)
+    LARGE_BUF_SIZE = 1 * 32 * 150000 * 128 * 2
+    MEDIUM_BUF_SIZE = 1 * 32 * 50000 * 128 * 2
+    SMALL_BUF_SIZE = 1 * 32 * 15000 * 128 * 2
+
+    def __init__(self, name: str, layer_num: int, dtype: torch.dtype, device, cpu_buf_size: int = 0):
+        flags = GLOBAL_CONFIG["offloading"]
+        if name not in flags:
+            raise ValueError(f"Invalid tensor name: {name}. Expected one of: {list(flags.keys())}")
+        self.name = name
+        self.layer_num = layer_num
+        self.dtype = dtype
+        self.device = device
+        self.is_offload_enabled = (not flags["global_disable_offloading"]) and bool(flags[name])
+        self.layer_key = layer_num % PIPELINE_DEPTH
+        n = _invocations()
+        self.gpu_tensor: List[Optional[torch.Tensor]] = [None] * n
+        self.cpu_buf: List[Optional[torch.Tensor]] = [None] * n
+        self.real_shape: List[Optional[torch.Size]] = [None] * n
+        self.model_invocation_count = 0
+        if self.is_offload_enabled:
+            _gpu_slots.setdefault(name, [None] * PIPELINE_DEPTH)
+
+    # ---- bookkeeping
+    def complete_cur_layer(self) -> None:
+        self.model_invocation_count += 1
+
+    def get_cur_model_invocation_key(self) -> int:
+        return self.model_invocation_count % _invocations()
+
+    # ---- store
+    @torch.compiler.disable
+    def offload(self, gpu_tensor: torch.Tensor) -> None:
+        key = self.get_cur_model_invocation_key()
+        if not self.is_offload_enabled:
+            self.gpu_tensor[key] = gpu_tensor
+            return
+        self.real_shape[key] = gpu_tensor.shape
+        buf = self.cpu_buf[key]
+        if buf is None or buf.numel() < gpu_tensor.numel() or buf.dtype != gpu_tensor.dtype:
+            buf = torch.empty(gpu_tensor.numel(), dtype=gpu_tensor.dtype, device="cpu", pin_memory=True)
+            self.cpu_buf[key] = buf
+        out = _stream("offload")
+        out.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(out):
+            buf[: gpu_tensor.numel()].view(gpu_tensor.shape).copy_(gpu_tensor, non_blocking=True)
+            gpu_tensor.record_stream(out)
+
+    def offload_cur_value(self) -> None:
+        self.offload(self.get_loaded_value())
+
+    # ---- fetch
+    def get_loaded_value(self) -> Optional[torch.Tensor]:
+        if not self.is_offload_enabled:
+            return self.gpu_tensor[self.get_cur_model_invocation_key()]
+        t = _gpu_slots[self.name][self.layer_key]
+        assert t is not None, (f"Tensor {self.name} is not loaded yet for layer {self.layer_num}. "
+                               "Call load_async() then load_async_wait() first")
+        return t
+
+    @torch.compiler.disable
+    def load_async(self) -> Optional[torch.Tensor]:
+        key = self.get_cur_model_invocation_key()
+        if not self.is_offload_enabled:
+            return self.gpu_tensor[key]
+        shape = self.real_shape[key]
+        if shape is None:
+            return None
+        ring = _gpu_slots[self.name]
+        if ring[self.layer_key] is None or ring[self.layer_key].shape != shape:
+            ring[self.layer_key] = torch.empty(shape, dtype=self.cpu_buf[key].dtype, device=self.device)
+        dst = ring[self.layer_key]
+        inp = _stream("load")
+        inp.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(inp):
+            dst.copy_(self.cpu_buf[key][: dst.numel()].view(shape), non_blocking=True)
+            dst.record_stream(_stream("offload"))
+        return dst
+
+    def load_async_wait(self) -> None:
+        if not self.is_offload_enabled:
+            return
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(_stream("load"))
+        cur.wait_stream(_stream("offload"))
+
+
+class _Slots:
+    """Attribute bag of MaybeOffloadedTensor with generated get_/set_ accessors."""
+
+    _prefix = ""
+    _names: tuple = ()
+
+    def __init__(self, layer_num: int):
+        self.layer_num = layer_num
+        for n in self._names:
+            setattr(self, n, None)
+
+    def _get(self, n):
+        slot = getattr(self, n)
+        return None if slot is None else slot.get_loaded_value()
+
+    def _set(self, n, value: torch.Tensor):
+        slot = getattr(self, n)
+        if slot is None:
+            slot = MaybeOffloadedTensor(f"{self._prefix}.{n}", self.layer_num, value.dtype, value.device)
+            setattr(self, n, slot)
+        slot.offload(value)
+
+    def _each(self, names=None):
+        for n in (names or self._names):
+            slot = getattr(self, n)
+            if slot is not None:
+                yield slot
+
+    def load_async(self):
+        for s in self._each(self._load_names):
+            s.load_async()
+
+    def load_async_wait(self):
+        for s in self._each(self._load_names):
+            s.load_async_wait()
+
+    def complete_cur_layer(self):
+        for s in self._each(self._complete_names):
+            s.complete_cur_layer()
+
+
+def _accessors(cls):
+    for n in cls._names:
+        setattr(cls, f"get_{n}", (lambda self, _n=n: self._get(_n)))
+        setattr(cls, f"set_{n}", (lambda self, value, _n=n: self._set(_n, value)))
+    return cls
+
+
+@_accessors
+class MlpStorage(_Slots):
+    """sparse_act_T [1,F,M], out_cache [1,M,N], indices [1,M/128,F], counts [1,M/128],
+    blockmean_mid_cache [1,M/128,F]  (reference layer_storage.py:5-99)."""
+    _prefix = "mlp"
+    _names = ("sparse_act_T", "out_cache", "indices", "counts", "blockmean_mid_cache")
+    _load_names = ("sparse_act_T", "out_cache", "indices", "counts")
+    _complete_names = ("blockmean_mid_cache", "out_cache", "indices", "counts")
+
+
+@_accessors
+class AttnStorage(_Slots):
+    """indices (bit-packed mask or int32 indices), counts, out_cache [B,H,N,128],
+    lse_constants [B,H,N,1]  (reference layer_storage.py:101-189)."""
+    _prefix = "attn"
+    _names = ("indices", "counts", "out_cache", "lse_constants")
+    _load_names = _names
+    _complete_names = _names
+
+    def __init__(self, layer_num: int, init_names=()):
+        super().__init__(layer_num)
+        # the reference pre-creates these two so that `storage.out_cache.is_offload_enabled`
+        # can be read before the first set (modules/attn.py:186)
+        dev = torch.device("cuda")
+        if "out_cache" in init_names:
+            self.out_cache = MaybeOffloadedTensor("attn.out_cache", layer_num, torch.bfloat16, dev)
+        if "indices" in init_names:
+            self.indices = MaybeOffloadedTensor("attn.indices", layer_num, torch.uint8, dev)
+
+
+class LayerStorage:
+    def __init__(self, layer_num: int):
+        self.layer_num = layer_num
+        self.mlp = MlpStorage(layer_num)
+        self.attn = AttnStorage(layer_num)
+
+    def load_async(self):
+        self.mlp.load_async()
+        self.attn.load_async()
+
+    def load_async_wait(self):
+        self.mlp.load_async_wait()
+        self.attn.load_async_wait()

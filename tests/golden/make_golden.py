@@ -1,0 +1,77 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own Python (run in the authoring container,
+where /root/reference exists; the fixtures are committed because the reference cannot travel
+to the GPU box).
+
+    python tests/golden/make_golden.py
+
+Sources imported by path (importing the `chipmunk` package itself fails without chipmunk.cuda):
+  * /root/reference/src/chipmunk/ops/bitpack.py   -> bitpack / bitunpack   (torch.compile is
+    replaced by the identity so the plain eager function runs on CPU)
+  * /root/reference/src/chipmunk/ops/voxel.py     -> masktoinds (the reference's pure-torch
+    statement of which index SET and which padded count mask_to_indices must produce)
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/src/chipmunk/ops"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(f"_ref_{name}", os.path.join(REF, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("reference not mounted; fixtures are already committed")
+    real_compile = torch.compile
+    torch.compile = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
+    try:
+        ref_bitpack = _load("bitpack")
+        ref_voxel = _load("voxel")
+    finally:
+        torch.compile = real_compile
+
+    g = torch.Generator().manual_seed(20260117)
+
+    # ---- bitpack / bitunpack: shapes incl. a non-multiple-of-8 element count
+    cases = {}
+    for i, shape in enumerate([(1, 2, 3, 37), (1, 3, 5, 192), (2, 2, 4, 500), (1, 1, 1, 7)]):
+        mask = torch.rand(shape, generator=g) < 0.3
+        packed, oshape = ref_bitpack.bitpack(mask)
+        back = ref_bitpack.bitunpack(packed, oshape)
+        assert torch.equal(back, mask)
+        cases[f"mask{i}"] = mask.numpy()
+        cases[f"packed{i}"] = packed.numpy()
+    np.savez_compressed(os.path.join(HERE, "bitpack.npz"), **cases)
+
+    # ---- masktoinds: index sets + padded counts for several densities and multiples
+    cases = {}
+    for i, (shape, dens, mult) in enumerate([
+        ((1, 2, 3, 384), 0.2, 128),
+        ((1, 2, 2, 500), 0.5, 112),
+        ((2, 1, 2, 1000), 0.07, 128),
+        ((1, 1, 2, 256), 0.0, 128),     # empty rows
+        ((1, 1, 2, 256), 1.0, 128),     # full rows
+    ]):
+        mask = torch.rand(shape, generator=g) < dens
+        inds, counts = ref_voxel.masktoinds(mask, multiple=mult)
+        nnz = mask.sum(dim=-1).to(torch.int32)
+        cases[f"mask{i}"] = mask.numpy()
+        cases[f"mult{i}"] = np.int32(mult)
+        cases[f"inds{i}"] = inds.numpy()          # first nnz entries of each row = the set columns
+        cases[f"counts{i}"] = counts.numpy()      # nnz rounded up to `mult`
+        cases[f"nnz{i}"] = nnz.numpy()
+    np.savez_compressed(os.path.join(HERE, "masktoinds.npz"), **cases)
+    print("wrote", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()
