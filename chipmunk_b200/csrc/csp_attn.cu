@@ -78,6 +78,79 @@ __device__ __forceinline__ int tile_count(const Params& P, int tile, bool dense)
     return c > (int)P.idx_row_stride ? (int)P.idx_row_stride : c;
 }
 
+// One softmax step of one query row (= one thread): S row (128 fp32 in TMEM) -> P row (bf16, written
+// over the first 64 columns of S).  m_ref is the row's reference maximum in raw score units; it is
+// only moved (and O / l rescaled) when the new tile maximum exceeds it by more than 2^8 after
+// scaling, so most steps skip the correction.  TAIL masks packed positions >= valid by position
+// (reference csp_attn.cu:272) by loading them as -inf.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref,
+                                             float& l_sum) {
+    uint32_t s[KT];
+#pragma unroll
+    for (int c = 0; c < KT; c += 32) tmem_ld32(tS + c, s + c);
+    tmem_ld_wait();
+    if (TAIL) {
+#pragma unroll
+        for (int j = 0; j < KT; j++) s[j] = j < valid ? s[j] : 0xff800000u;
+    }
+    // ---- tile max: 4 independent chains of 3-input max
+    float mx[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        mx[c] = __uint_as_float(s[c * 32]);
+#pragma unroll
+        for (int j = 1; j < 31; j += 2)
+            mx[c] = fmax3(mx[c], __uint_as_float(s[c * 32 + j]), __uint_as_float(s[c * 32 + j + 1]));
+        mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 32 + 31]));
+    }
+    const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    // ---- lazy rescale of the running state (always taken on the first step: m_ref = -inf)
+    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
+    if (__any_sync(0xffffffffu, need)) {
+        float alpha = 1.f;
+        if (need) {
+            alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);
+            m_ref = m_tile;
+            l_sum *= alpha;
+        }
+        if (kk > 0) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tO + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+                tmem_st_32x32b_x32(tO + c0, r);
+            }
+        }
+    }
+    // ---- P = exp2(s*c - m*c) (packed fp32x2 FMA), row sum, bf16 pack, write over S
+    const float neg_m = -m_ref * SCALE_LOG2;
+    const uint64_t c2 = pack_f32x2(SCALE_LOG2, SCALE_LOG2), nm2 = pack_f32x2(neg_m, neg_m);
+    uint64_t acc[2] = {0ull, 0ull};
+    const int cols = TAIL ? ((valid + 15) & ~15) : KT;
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const uint64_t x = ffma2(pack_f32x2(__uint_as_float(s[c0 + j]), __uint_as_float(s[c0 + j + 1])), c2, nm2);
+            float x0, x1;
+            unpack_f32x2(x, x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            acc[(j >> 1) & 1] = fadd2(acc[(j >> 1) & 1], pack_f32x2(p0, p1));
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+        if (!TAIL || c0 < cols) tmem_st_32x32b_x16(tS + (c0 >> 1), pk);
+    }
+    float a0, a1, a2, a3;
+    unpack_f32x2(acc[0], a0, a1);
+    unpack_f32x2(acc[1], a2, a3);
+    l_sum += (a0 + a1) + (a2 + a3);
+}
+
 // ------------------------------------------------------------------------------------------
 template <bool DENSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
@@ -107,6 +180,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
 
     // =========================================================================== producers
     if (warp >= WARP_PROD0) {
+        setmaxnreg_dec<80>();
         const int pt = tid - WARP_PROD0 * 32;       // 0..127
         const int chunk = pt & 15;                  // 16-byte chunk of the 256-byte row
         const int rsub = pt >> 4;                   // 0..7
@@ -136,30 +210,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             const __nv_bfloat16* vb = P.v + b * P.vs[0] + h * P.vs[1];
             const int32_t* ip = DENSE ? nullptr : P.indices + (int64_t)tile * P.idx_row_stride;
             const int nk = (count + KT - 1) / KT;
+            // Lane j of producer warp w fetches the index of key row (2w + (j>>4)) + 8*(j&15) of the
+            // step: one coalesced-ish load per thread per step, issued one step ahead; the 16 rows a
+            // thread copies are then read from its half-warp with shuffles.
+            const int my_r = rsub + 8 * (lane & 15);
+            auto fetch_idx = [&](int kk) -> int {
+                const int pos = kk * KT + my_r;
+                int idx = pos;
+                if (!DENSE) idx = pos < count ? __ldg(ip + pos) : 0;
+                idx = idx < 0 ? 0 : (idx >= P.Nk ? P.Nk - 1 : idx);
+                return pos < count ? idx : -1;
+            };
+            int idx_next = fetch_idx(0);
             for (int kk = 0; kk < nk; kk++) {
-                int64_t off[KT / 8];
-                uint32_t okm = 0;
+                const int idx_cur = idx_next;
+                if (kk + 1 < nk) idx_next = fetch_idx(kk + 1);
+                int rowidx[KT / 8];
 #pragma unroll
-                for (int i = 0; i < KT / 8; i++) {
-                    const int pos = kk * KT + rsub + 8 * i;
-                    const bool ok = pos < count;
-                    int idx = DENSE ? pos : (ok ? __ldg(ip + pos) : 0);
-                    idx = idx < 0 ? 0 : (idx >= P.Nk ? P.Nk - 1 : idx);
-                    off[i] = ok ? (int64_t)idx : -1;
-                    okm |= (ok ? 1u : 0u) << i;
-                }
+                for (int i = 0; i < KT / 8; i++) rowidx[i] = __shfl_sync(0xffffffffu, idx_cur, (lane & 16) + i);
 #pragma unroll
                 for (int op = 0; op < 2; op++) {
                     const uint32_t slot = job % NSLOT;
                     mbar_wait(&bar.kv_empty[slot], ((job / NSLOT) & 1) ^ 1);
                     const uint32_t dst0 = sKV + slot * SLOT_BYTES + half_off * (SLOT_BYTES / 2);
-                    const __nv_bfloat16* base = op == 0 ? kb : vb;
+                    const __nv_bfloat16* base = (op == 0 ? kb : vb) + chunk * 8;
                     const int64_t rs = op == 0 ? P.ks[2] : P.vs[2];
 #pragma unroll
                     for (int i = 0; i < KT / 8; i++) {
                         const int r = rsub + 8 * i;
-                        const bool ok = (okm >> i) & 1u;
-                        const __nv_bfloat16* src = base + (ok ? off[i] : 0) * rs + chunk * 8;
+                        const bool ok = rowidx[i] >= 0;
+                        const __nv_bfloat16* src = base + (int64_t)(ok ? rowidx[i] : 0) * rs;
                         cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&bar.kv_full[slot]);
@@ -171,6 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
+        setmaxnreg_inc<208>();
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
         const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
@@ -249,6 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
     }
     // =========================================================================== softmax + epilogue
     else if (warp < 6) {
+        setmaxnreg_inc<208>();
         const int blk = warp >> 2;                         // 0: rows 0-127, 1: rows 128-191
         const int r_in_tile = blk * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -275,59 +357,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
 
             for (int kk = 0; kk < nk; kk++) {
                 const int valid = min(KT, count - kk * KT);
-                const int cols = (valid + 15) & ~15;
                 mbar_wait(&bar.s_full[blk], sc & 1); sc++;
                 tc_fence_after_sync();
-                // ---- pass 1: tile max
-                float m_tile = -INFINITY;
-                for (int c0 = 0; c0 < cols; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tS + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float s = __uint_as_float(r[j]);
-                        m_tile = (c0 + j < valid) ? fmaxf(m_tile, s) : m_tile;
-                    }
-                }
-                // ---- lazy rescale of the running state
-                const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;   // true on the first step
-                if (__any_sync(0xffffffffu, need)) {
-                    float alpha = 1.f;
-                    if (need) {
-                        alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);   // exp2(-inf) = 0 on the first step
-                        m_ref = m_tile;
-                        l_sum *= alpha;
-                    }
-                    if (kk > 0) {
-                        for (int c0 = 0; c0 < D; c0 += 32) {
-                            uint32_t r[32];
-                            tmem_ld_32x32b_x32(tO + c0, r);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-                            tmem_st_32x32b_x32(tO + c0, r);
-                        }
-                    }
-                }
-                const float neg_m = -m_ref * SCALE_LOG2;
-                // ---- pass 2: P = exp2(s*c - m*c), row sum, bf16 pack, write over S
-                for (int c0 = 0; c0 < cols; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tS + c0, r);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float p0 = fast_exp2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, neg_m));
-                        float p1 = fast_exp2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, neg_m));
-                        p0 = (c0 + j < valid) ? p0 : 0.f;
-                        p1 = (c0 + j + 1 < valid) ? p1 : 0.f;
-                        l_sum += p0 + p1;
-                        pk[j >> 1] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st_32x32b_x16(tS + (c0 >> 1), pk);
-                }
+                if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
+                else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 mbar_arrive(&bar.p_full[blk]);
@@ -363,6 +396,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             tc_fence_before_sync();
         }
     }
+    else {
+        setmaxnreg_inc<208>();      // warp 7: idle, but setmaxnreg is warpgroup-wide
+    }
+
     tc_fence_before_sync();
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc(tm, 512);

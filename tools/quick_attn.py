@@ -43,8 +43,13 @@ def run(B, H, N, count, iters=10):
         print(f"    torch SDPA dense: {ms2*1e3:.1f} us ({dense/ms2/1e9:.0f} TFLOP/s) -> speedup {ms2/ms:.2f}x", flush=True)
 
 if __name__ == "__main__":
-    run(2, 24, 4096, 768)
-    run(1, 24, 4608, 672)
-    run(1, 24, 16384, 2944)
-    if len(sys.argv) > 1:
-        run(1, 24, 119056, 8320, iters=2)
+    if len(sys.argv) >= 3:
+        N, count = int(sys.argv[1]), int(sys.argv[2])
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+        H = int(sys.argv[4]) if len(sys.argv) > 4 else 24
+        it = int(sys.argv[5]) if len(sys.argv) > 5 else 10
+        run(B, H, N, count, iters=it)
+    else:
+        run(2, 24, 4096, 768)
+        run(1, 24, 4608, 672)
+        run(1, 24, 16384, 2944)
