@@ -31,3 +31,31 @@ extern "C" const char* cm_strerror(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "chipmunk_b200: unknown error";
 }
+
+// ------------------------------------------------------------------------------------------
+#include "tma.cuh"
+namespace cm {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int encode_tmap_2d_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t pitch_bytes, uint32_t box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) return e != cudaSuccess ? (int)e : (int)cudaErrorSymbolNotFound;
+        g_encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {pitch_bytes};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+}  // namespace cm

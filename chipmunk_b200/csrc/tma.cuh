@@ -1,0 +1,31 @@
+// TMA (cp.async.bulk.tensor) helpers: host-side tensor-map encoding without linking libcuda
+// (the driver entry point is fetched through the runtime), and the device-side 2-D tile load.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace cm {
+
+// Encode a row-major 2-D bf16 tensor [rows, cols] (row pitch `pitch_bytes`) whose tiles of
+// `box_rows` x 64 columns land in shared memory as [box_rows][128 B] with SWIZZLE_128B -- the
+// K-major operand layout tcgen05.mma reads (see ptx.cuh: umma_smem_desc).
+// Returns 0 or a CUresult.
+int encode_tmap_2d_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t pitch_bytes, uint32_t box_rows);
+
+// One thread: load the tile whose top-left element is (row, col) into `dst` (1024-byte aligned),
+// completing `bytes` on `bar`.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::1 "
+        "[%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
+}  // namespace cm

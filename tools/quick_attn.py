@@ -34,7 +34,7 @@ def run(B, H, N, count, iters=10):
     print(f"N={N} H={H} B={B} count={count}: {ms*1e3:.1f} us  sparse {flops/ms/1e9:.0f} TFLOP/s  "
           f"dense-equiv {dense/ms/1e9:.0f} TFLOP/s  gather {gbytes/ms*1e3:.0f} GB/s", flush=True)
     # dense baseline (torch SDPA)
-    if N <= 20000:
+    if N <= 130000:
         for _ in range(2): torch.nn.functional.scaled_dot_product_attention(q, k, v)
         torch.cuda.synchronize(); e0.record()
         for _ in range(5): torch.nn.functional.scaled_dot_product_attention(q, k, v)
