@@ -5,6 +5,11 @@
 // computed TRANSPOSED on the tensor pipe, S^T = K_tile Q_g^T (M = 128 keys on the TMEM lanes,
 // N = 192 queries on the columns), so the sum over the group's queries is a per-thread loop
 // over TMEM columns: no atomics, no shuffles, fp32 accumulation, one bf16 rounding.
+//
+//   warp 5     TMA: Q group tile once per (b,h,g) (double-buffered), K tiles through a 3-stage ring
+//   warp 4     MMA issuer: tcgen05.mma M=128 N=192 K=128 into one of two TMEM accumulators
+//   warps 0-3  one thread per key: sum_i exp2(s*c + log2 p_i) over the 192 columns, bf16 store
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,14 +17,181 @@
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma.cuh"
 
 namespace cm {
 namespace attn {
 
-int launch_colsum(const __nv_bfloat16* q, const __nv_bfloat16* k, const float* p, __nv_bfloat16* cs, int B, int H,
+namespace cs {
+constexpr int D = 128, QG = 192, KT = 128;
+constexpr int Q_BYTES = 2 * QG * 128;       // 49152: two 64-wide d-halves
+constexpr int K_BYTES = 2 * KT * 128;       // 32768
+constexpr int KSTAGES = 3;
+constexpr int SMEM_BYTES = 2 * Q_BYTES + KSTAGES * K_BYTES + 1024;
+constexpr int NUM_THREADS = 192;
+constexpr float SCALE_LOG2 = 0.08838834764f * 1.44269504089f;
+
+struct Params {
+    const float* p;            // [B*H, Nq]
+    __nv_bfloat16* cs;         // [B*H*G, cs_stride]
+    int BH, Nq, Nk, G;
+    int64_t cs_stride;
+    int num_tiles, n_kt;
+};
+
+struct __align__(8) Barriers {
+    uint64_t q_full[2], q_empty[2];
+    uint64_t k_full[KSTAGES], k_empty[KSTAGES];
+    uint64_t acc_full[2], acc_empty[2];
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_lp[2][QG];     // log2(p_i) of the tile's query rows
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = sbase, sK = sbase + 2 * Q_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&bar.q_full[i], 1); mbar_init(&bar.q_empty[i], 1);
+            mbar_init(&bar.acc_full[i], 1); mbar_init(&bar.acc_empty[i], 128);
+        }
+        for (int i = 0; i < KSTAGES; i++) { mbar_init(&bar.k_full[i], 1); mbar_init(&bar.k_empty[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 4) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = tmem_base_s;
+
+    if (warp == 5) {
+        // ======================================================================= TMA loader
+        if (lane == 0) {
+            uint32_t tcount = 0, kc = 0;
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, tcount++) {
+                const int g = tile % P.G, bh = tile / P.G;
+                const uint32_t qb = tcount & 1;
+                mbar_wait(&bar.q_empty[qb], ((tcount >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bar.q_full[qb], Q_BYTES);
+                const int qrow = bh * P.Nq + g * QG;
+                tma_load_2d(sQ + qb * Q_BYTES, &tmap_q, &bar.q_full[qb], 0, qrow);
+                tma_load_2d(sQ + qb * Q_BYTES + Q_BYTES / 2, &tmap_q, &bar.q_full[qb], 64, qrow);
+                for (int kt = 0; kt < P.n_kt; kt++, kc++) {
+                    const uint32_t s = kc % KSTAGES;
+                    mbar_wait(&bar.k_empty[s], ((kc / KSTAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar.k_full[s], K_BYTES);
+                    const int krow = bh * P.Nk + kt * KT;
+                    tma_load_2d(sK + s * K_BYTES, &tmap_k, &bar.k_full[s], 0, krow);
+                    tma_load_2d(sK + s * K_BYTES + K_BYTES / 2, &tmap_k, &bar.k_full[s], 64, krow);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ======================================================================= MMA issuer
+        uint32_t tcount = 0, kc = 0;
+        const uint32_t idesc = umma_idesc_bf16(KT, QG, 0, 0);
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, tcount++) {
+            const uint32_t qb = tcount & 1;
+            mbar_wait(&bar.q_full[qb], (tcount >> 1) & 1);
+            for (int kt = 0; kt < P.n_kt; kt++, kc++) {
+                const uint32_t s = kc % KSTAGES, ab = kc & 1;
+                mbar_wait(&bar.k_full[s], (kc / KSTAGES) & 1);
+                mbar_wait(&bar.acc_empty[ab], ((kc >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k16 = 0; k16 < D / 16; k16++) {
+                        const uint64_t ad = umma_smem_desc(sK + s * K_BYTES + (k16 >> 2) * (K_BYTES / 2) + (k16 & 3) * 32, 16, 1024);
+                        const uint64_t bd = umma_smem_desc(sQ + qb * Q_BYTES + (k16 >> 2) * (Q_BYTES / 2) + (k16 & 3) * 32, 16, 1024);
+                        umma_ss(tm + ab * 256, ad, bd, idesc, k16 > 0);
+                    }
+                    umma_commit(&bar.k_empty[s]);
+                    umma_commit(&bar.acc_full[ab]);
+                    if (kt == P.n_kt - 1) umma_commit(&bar.q_empty[qb]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ======================================================================= exp + column sum
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const int key_in_tile = warp * 32 + lane;
+        uint32_t tcount = 0, kc = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, tcount++) {
+            const int g = tile % P.G, bh = tile / P.G;
+            const uint32_t lb = tcount & 1;
+            for (int i = tid; i < QG; i += 128) {
+                const int row = g * QG + i;
+                const float pv = row < P.Nq ? __ldg(P.p + (int64_t)bh * P.Nq + row) : 0.f;
+                s_lp[lb][i] = pv > 0.f ? __log2f(pv) : -INFINITY;
+            }
+            named_bar_sync(1, 128);
+            __nv_bfloat16* crow = P.cs + (int64_t)tile * P.cs_stride;
+            for (int kt = 0; kt < P.n_kt; kt++, kc++) {
+                const uint32_t ab = kc & 1;
+                mbar_wait(&bar.acc_full[ab], (kc >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t tacc = tm + ab * 256 + lane_off;
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < QG; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tacc + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 lp = *reinterpret_cast<const float4*>(&s_lp[lb][c0 + j]);
+                        acc0 += fast_exp2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, lp.x));
+                        acc1 += fast_exp2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, lp.y));
+                        acc0 += fast_exp2(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, lp.z));
+                        acc1 += fast_exp2(fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, lp.w));
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bar.acc_empty[ab]);
+                const int key = kt * KT + key_in_tile;
+                if (key < P.Nk) crow[key] = __float2bfloat16(acc0 + acc1);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tm, 512);
+}
+}  // namespace cs
+
+int launch_colsum(const __nv_bfloat16* q, const __nv_bfloat16* k, const float* p, __nv_bfloat16* cs_out, int B, int H,
                   int Nq, int Nk, int64_t cs_row_stride, cudaStream_t stream) {
-    (void)q; (void)k; (void)p; (void)cs; (void)B; (void)H; (void)Nq; (void)Nk; (void)cs_row_stride; (void)stream;
-    return CM_EUNSUPPORTED;   // filled in below once the main attention kernel is validated
+    using namespace cs;
+    CUtensorMap tq, tk;
+    int rc = encode_tmap_2d_bf16_sw128(&tq, q, (uint64_t)B * H * Nq, D, D * 2, QG);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16_sw128(&tk, k, (uint64_t)B * H * Nk, D, D * 2, KT);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    Params P{};
+    P.p = p; P.cs = cs_out; P.BH = B * H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
+    P.cs_stride = cs_row_stride;
+    const int64_t tiles = (int64_t)B * H * P.G;
+    if (tiles > 2147483647ll) return CM_EINVAL;
+    P.num_tiles = (int)tiles;
+    P.n_kt = (Nk + KT - 1) / KT;
+    const int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
+    colsum_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tk, P);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace attn

@@ -126,3 +126,27 @@ def test_dense_attn_matches_oracle_and_sdpa(cm, oracle, cuda, B, H, N):
     assert l.shape == (B, H, N, 1) and l.dtype == torch.float32
     torch.testing.assert_close(l.cpu(), rl, rtol=2e-3, atol=0)
     _close(o, oracle.sdpa(q, k, v).to(torch.bfloat16), rel=6e-3, ulps=3)   # reference test_dense_attn.py:29-34
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 2, 384), (1, 2, 500), (2, 1, 1000)])
+def test_dense_colsum_attn_matches_oracle(cm, oracle, cuda, B, H, N):
+    """o, l as dense_attn; cs = per-192-row-group column sums of exp(s)*p (reference
+    dense_colsum_attn.cu:267-277 accumulates them in bf16 with atomics; kernel and oracle
+    accumulate in fp32 and round once, so they agree to bf16 rounding: 1 ulp = 2^-8 relative)."""
+    gen = torch.Generator().manual_seed(N + 5)
+    q, k, v = _rand_qkv(B, H, N, N, gen)
+    # p = l of a slightly different q, as on consecutive denoising steps
+    q_prev = (q.float() + 0.05 * torch.randn(q.shape, generator=gen)).to(torch.bfloat16)
+    _, p = oracle.dense_attn(q_prev, k, v)
+    ro, rcs, rl = oracle.dense_colsum_attn(q, k, v, p)
+    o, cs, l = torch.ops.chipmunk.dense_colsum_attn(q.to(cuda), k.to(cuda), v.to(cuda), p.to(cuda))
+    _close(o, ro)
+    torch.testing.assert_close(l.cpu(), rl, rtol=2e-3, atol=0)
+    G = (N + 191) // 192
+    assert cs.shape == (B, H, G, N) and cs.dtype == torch.bfloat16
+    torch.testing.assert_close(cs.float().cpu(), rcs.float(), rtol=1.2e-2, atol=1e-6)
+    # wrapper with padded p (what SparseDiffAttn passes): same values
+    pn = ((N + 191) // 192) * 192
+    pp = torch.zeros(B, H, pn, 1); pp[:, :, :N] = p
+    o2, cs2, l2 = cm.ops.dense_colsum_attn(q.to(cuda), k.to(cuda), v.to(cuda), pp.to(cuda))
+    assert torch.equal(cs2, cs[..., : (N + 191) // 192, :N]) and l2.shape[-2] == pn
