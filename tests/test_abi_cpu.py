@@ -1,0 +1,130 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/chipmunk_b200.h declares (no compute calls without a GPU), the operator schemas are
+registered under torch.ops.chipmunk, and the host-side state objects behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "chipmunk_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(cm):
+    lib = ctypes.CDLL(os.path.join(ROOT, "chipmunk_b200", "libchipmunk_b200.so"))
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/chipmunk_b200.h but not exported"
+    assert set(syms) == set(cm._lib.EXPORTS)
+    assert lib.cm_abi_version() == 1
+    lib.cm_strerror.restype = ctypes.c_char_p
+    assert b"16-byte" in lib.cm_strerror(-2)
+
+
+def test_argument_validation_needs_no_gpu(cm):
+    """Entry points reject bad arguments before touching the device."""
+    lib = cm._lib.lib
+    assert lib.cm_bitpack(None, None, -1, None) == -1
+    assert lib.cm_mask_to_indices(None, None, None, 4, 0, 0, 128, None) == -1
+    assert lib.cm_topk_indices(None, 0, None, None, 1, 1, 0, 0.5, 256, 0.0, None) == -1
+    assert lib.cm_csp_mlp_mm1(None, None, None, None, None, None, None, 100, 64, 256, 256, 0, None) == -1
+    s3 = (ctypes.c_int64 * 3)(8, 8, 8)
+    assert lib.cm_csp_attn(None, None, None, None, None, None, 1, 1, 192, 192, s3, s3, s3, s3, 192, 3, 1, None) == -1
+
+
+def test_operator_schemas_registered(cm):
+    want = {
+        "csp_mlp_mm1": 7, "csp_mlp_mm2_and_scatter_add": 9, "csp_attn": 7, "csp_128_attn": 5, "dense_attn": 3,
+        "dense_colsum_attn": 4, "copy_indices": 4, "topk_indices": 6, "csp_scatter_add": 5, "mask_to_indices": 3,
+    }
+    for name, nargs in want.items():
+        op = getattr(torch.ops.chipmunk, name)
+        schema = op.default._schema
+        assert len(schema.arguments) == nargs, (name, str(schema))
+    s = str(torch.ops.chipmunk.csp_attn.default._schema)
+    assert "int o_scale" in s and "Tensor indices_counts" in s
+    s = str(torch.ops.chipmunk.mask_to_indices.default._schema)
+    assert "int multiple_of, int pad_to_multiple_of" in s and "Tensor[]" in s
+
+
+def test_no_cpu_fallback(cm):
+    q = torch.zeros(1, 1, 192, 128, dtype=torch.bfloat16)
+    idx = torch.zeros(1, 1, 1, 192, dtype=torch.int32)
+    cnt = torch.zeros(1, 1, 1, dtype=torch.int32)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.chipmunk.csp_128_attn(q, q, q, idx, cnt)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cm.ops.bitpack(torch.zeros(8, dtype=torch.bool))
+
+
+def test_product_never_imports_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "chipmunk_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_layer_counter_schedule(cm):
+    from chipmunk_b200.util import GLOBAL_CONFIG
+    from chipmunk_b200.util.config import reset_to_defaults
+    from chipmunk_b200.util.layer_counter import LayerCounter
+
+    reset_to_defaults()
+    GLOBAL_CONFIG["steps"] = 4
+    c = LayerCounter(num_layers=2, num_sparse_submodules_per_layer=2)
+    seen, full_attn, full_mlp = [], [], []
+    for _ in range(4 * 2 * 2):
+        full_attn.append(c.should_do_full_attn_step()); full_mlp.append(c.should_do_full_mlp_step())
+        seen.append(c.increment())
+    assert seen[0] == (0, 0, 0) and seen[1] == (0, 0, 1) and seen[2] == (0, 1, 0) and seen[4] == (1, 0, 0)
+    assert full_attn[:8] == [True] * 8 and full_attn[8:12] == [False] * 4       # steps 0,1 full, step 2 sparse
+    assert full_mlp[:4] == [True] * 4 and full_mlp[4] is False
+    assert c.get_cur_coord() == (0, 0, 0) or c.cur_inference_step in (0, 3)      # rewinds at the end of a generation
+    GLOBAL_CONFIG["attn"]["full_step_schedule"] = {0, 3}
+    c.reset(); c.cur_inference_step = 3
+    assert c.should_do_full_attn_step()
+    c.cur_inference_step = 1
+    assert not c.should_do_full_attn_step()
+    reset_to_defaults()
+
+
+def test_config_deep_merge(cm, tmp_path):
+    from chipmunk_b200.util import GLOBAL_CONFIG, load_from_file
+    from chipmunk_b200.util.config import reset_to_defaults
+
+    reset_to_defaults()
+    p = tmp_path / "c.yml"
+    p.write_text("attn:\n  top_keys: 0.165\n  counts_multiple_of: 112\n  pad_qkv_before_kernel: false\nmlp:\n  top_keys: 0.3\n")
+    load_from_file(str(p))
+    assert GLOBAL_CONFIG["attn"]["top_keys"] == 0.165 and GLOBAL_CONFIG["attn"]["mbm"] == 192
+    assert GLOBAL_CONFIG["mlp"]["top_keys"] == 0.3 and GLOBAL_CONFIG["mlp"]["counts_multiple_of"] == 256
+    reset_to_defaults()
+
+
+def test_storage_resident_mode(cm):
+    from chipmunk_b200.util import AttnStorage, MlpStorage
+    from chipmunk_b200.util.config import reset_to_defaults
+
+    reset_to_defaults()
+    s = MlpStorage(3)
+    assert s.get_indices() is None
+    t = torch.arange(6).reshape(1, 2, 3)
+    s.set_indices(t)
+    assert s.get_indices() is t
+    s.load_async(); s.load_async_wait(); s.complete_cur_layer()
+    a = AttnStorage(0, init_names=["indices", "out_cache"])
+    assert a.out_cache is not None and a.out_cache.is_offload_enabled is False
+    a.set_out_cache(t)
+    assert a.get_out_cache() is t
+    with pytest.raises(ValueError):
+        from chipmunk_b200.util import MaybeOffloadedTensor
+        MaybeOffloadedTensor("attn.bogus", 0, torch.float32, "cpu")
