@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
@@ -63,6 +64,7 @@ struct Params {
     float o_scale;
     int accumulate;
     int num_tiles;
+    int dbg;                     // CM_DEBUG_FLAGS: timing experiments only (results are wrong when set)
 };
 
 struct __align__(8) Barriers {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                         const int r = rsub + 8 * i;
                         const bool ok = rowidx[i] >= 0;
                         const __nv_bfloat16* src = base + (int64_t)(ok ? rowidx[i] : 0) * rs;
-                        cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+                        if (!(P.dbg & 1)) cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&bar.kv_full[slot]);
                     job++;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                 const uint32_t idesc = umma_idesc_bf16(128, cols, 0, 0);
                 const uint32_t d = tm + (blk ? TM_S1 : TM_S0);
 #pragma unroll
-                for (int k16 = 0; k16 < D / 16; k16++) {
+                for (int k16 = 0; k16 < ((P.dbg & 2) ? 0 : D / 16); k16++) {
                     uint64_t ad = umma_smem_desc(sQ + (k16 >> 2) * Q_HALF_BYTES + blk * (128 * 128) + (k16 & 3) * 32, 16, 1024);
                     uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + (k16 >> 2) * (SLOT_BYTES / 2) + (k16 & 3) * 32, 16, 1024);
                     umma_ss(d, ad, bd, idesc, k16 > 0);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             auto issue_PV = [&](int blk, uint32_t slot, int cols, bool first) {
                 const uint32_t d = tm + (blk ? TM_O1 : TM_O0);
                 const uint32_t a = tm + (blk ? TM_S1 : TM_S0);
-                for (int j = 0; j < cols / 16; j++) {
+                for (int j = 0; j < ((P.dbg & 2) ? 0 : cols / 16); j++) {
                     uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + j * 2048, SLOT_BYTES / 2, 1024);
                     umma_ts(d, a + j * 8, bd, idesc_pv, (!first) || j > 0);
                 }
@@ -359,7 +361,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                 const int valid = min(KT, count - kk * KT);
                 mbar_wait(&bar.s_full[blk], sc & 1); sc++;
                 tc_fence_after_sync();
-                if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
+                if (P.dbg & 4) { l_sum = 1.f; }
+                else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
                 else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum);
                 tmem_st_wait();
                 tc_fence_before_sync();
@@ -455,6 +458,7 @@ extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
+    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
     return launch_attn<false>(P, (cudaStream_t)stream);
 }
 

@@ -3,11 +3,12 @@
 // Replaces csrc/mlp/csp_mlp_mm1.cu (Hopper wgmma), the Triton mm2 kernel and the CUDA-graph
 // launcher csrc/mlp/csp_mlp_mm2_and_scatter_add.cu, and csrc/indexed_io/scatter_add.cu.
 //
-// Both GEMMs share one persistent, warp-specialised skeleton (one CTA per SM, 384 threads):
-//     warps 0-3   epilogue: TMEM accumulator -> registers -> fused elementwise -> global
-//     warp  4     MMA issuer (one thread): tcgen05.mma M=128, N<=256, fp32 accumulators in TMEM,
+// Both GEMMs share one persistent, warp-specialised skeleton (one CTA per SM, 512 threads):
+//     warps 0-7   epilogue (2 warpgroups x 128 columns): TMEM accumulator -> registers -> fused elementwise -> global,
+//                 with the cache / output tile prefetched one 32-column chunk ahead
+//     warp  12    MMA issuer (one thread): tcgen05.mma M=128, N<=256, fp32 accumulators in TMEM,
 //                 two 256-column accumulator buffers so tile i+1's main loop overlaps tile i's epilogue
-//     warp  5     TMA: the dense operand tile (tokens x 64 of K) per stage
+//     warp  13    TMA: the dense operand tile (tokens x 64 of K) per stage
 //     warps 8-11  gather producers: the ACTIVE weight rows of this 128-token block, copied by index
 //                 with 16-byte cp.async into 128B-swizzled shared memory, i.e. the column-sparse
 //                 operand becomes a dense tensor-core tile
@@ -17,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
@@ -29,13 +31,14 @@ namespace mlp {
 constexpr int BM = 128;            // token rows per tile (= MLP index group)
 constexpr int BN = 256;            // output columns per tile
 constexpr int BK = 64;             // K elements per stage (128 bytes)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * 128;  // 16 KB
 constexpr int B_BYTES = BN * 128;  // 32 KB (mm1: 256 rows x 128 B; mm2: 4 n-chunks x 64 rows x 128 B)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-constexpr int NUM_THREADS = 384;
-constexpr int WARP_MMA = 4, WARP_TMA = 5, WARP_PROD0 = 8;
+constexpr int SMEM_MM1 = 4 * STAGE_BYTES + 1024;
+constexpr int SMEM_MM2 = 4 * STAGE_BYTES + 1024;
+constexpr int NUM_THREADS = 512;   // warps 0-7 epilogue (two warpgroups, 128 columns each) | 8-11 gather | 12 MMA | 13 TMA | 14-15 idle
+constexpr int WARP_MMA = 12, WARP_TMA = 13, WARP_PROD0 = 8, NUM_EPI = 256;
 
 struct Params {
     // mm1: a = tokens [M,K] (TMA), w = W1 [F,K], out = C [M,F] packed, bias [F], pa_T [F,M]
@@ -50,10 +53,11 @@ struct Params {
     int64_t idx_stride;
     int update_pa;
     int n_mb, n_nb;            // tile grid
+    int dbg;                   // CM_DEBUG_FLAGS (timing experiments only; results are wrong when set)
 };
 
 struct __align__(8) Barriers {
-    uint64_t full[STAGES], empty[STAGES];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
     uint64_t acc_full[2], acc_empty[2];
 };
 
@@ -73,12 +77,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
     __shared__ int s_idx[2][BN];          // mm1 epilogue: neuron index of each packed column of the tile
     __shared__ float s_bias[2][BN];       // mm1 epilogue: its bias
 
+    constexpr int STAGES = 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; i++) { mbar_init(&bar.full[i], 128 + 1); mbar_init(&bar.empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&bar.acc_full[i], 1); mbar_init(&bar.acc_empty[i], 128); }
+        for (int i = 0; i < 2; i++) { mbar_init(&bar.acc_full[i], 1); mbar_init(&bar.acc_empty[i], NUM_EPI); }
         fence_mbar_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
@@ -110,8 +115,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
     };
 
     // =========================================================================== gather producers
-    if (warp >= WARP_PROD0) {
-        setmaxnreg_dec<96>();
+    if (warp >= WARP_PROD0 && warp < WARP_PROD0 + 4) {
+        setmaxnreg_dec<88>();
         const int pt = tid - WARP_PROD0 * 32;
         uint32_t it = 0;       // global stage counter
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const int r = r0 + 16 * i;
-                        if ((okm >> i) & 1u)
+                        if (((okm >> i) & 1u) && !(P.dbg & 1))
                             cp_async_16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src[i] + ks * BK);
                     }
                     cp_async_mbar_arrive_noinc(&bar.full[s]);
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                     for (int i = 0; i < 16; i++) {
                         const int r = w + 4 * i;
                         const int f = __shfl_sync(0xffffffffu, f_cur, i);
-                        if (f >= 0) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
+                        if (f >= 0 && !(P.dbg & 1)) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
                     }
                     cp_async_mbar_arrive_noinc(&bar.full[s]);
                 }
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
     }
     // =========================================================================== TMA (dense operand)
     else if (warp == WARP_TMA) {
-        setmaxnreg_dec<96>();
+        setmaxnreg_dec<88>();
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 for (int ks = 0; ks < ksteps; ks++, it++) {
                     const uint32_t s = it % STAGES;
                     mbar_wait(&bar.empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (P.dbg & 2) { mbar_arrive(&bar.full[s]); continue; }
                     mbar_arrive_expect_tx(&bar.full[s], A_BYTES);
                     tma_load_2d(sbase + s * STAGE_BYTES, &tmap_a, &bar.full[s], ks * BK, mb * BM);
                 }
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
-        setmaxnreg_dec<96>();
+        setmaxnreg_dec<88>();
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mb, nb, ncols, ksteps, klast;
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 if (lane == 0) {
                     const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
                     const int k16s = (ks == ksteps - 1 ? klast : BK) / 16;
-                    for (int k16 = 0; k16 < k16s; k16++) {
+                    for (int k16 = 0; k16 < ((P.dbg & 4) ? 0 : k16s); k16++) {
                         const uint64_t ad = umma_smem_desc(sa + k16 * 32, 16, 1024);
                         const uint64_t bd = IS_MM2 ? umma_smem_desc(sb + k16 * 2048, BK * 128, 1024)
                                                    : umma_smem_desc(sb + k16 * 32, 16, 1024);
@@ -229,71 +235,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         }
     }
     // =========================================================================== epilogue
-    else if (warp < 4) {
-        setmaxnreg_inc<200>();
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    else if (warp < 8) {
+        setmaxnreg_inc<152>();
+        const int wq = warp & 3, half = warp >> 2;           // TMEM lane quadrant, column half of the tile
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mb, nb, ncols, ksteps, klast;
             tile_shape(tile, mb, nb, ncols, ksteps, klast);
             if (ncols <= 0) continue;
             const uint32_t buf = tcount & 1;
-            const int m = mb * BM + warp * 32 + lane;
+            const int m = mb * BM + wq * 32 + lane;
+            const int cbeg = half * (BN / 2);
+            const int cend = min(ncols, cbeg + BN / 2);
             if (!IS_MM2) {
-                // stage this tile's neuron ids and biases (the 128 epilogue threads, 2 columns each)
+                // stage this tile's neuron ids and biases (256 epilogue threads, one column each)
                 const int32_t* ip = P.indices + (int64_t)mb * P.idx_stride + nb * BN;
-                for (int c = tid; c < BN; c += 128) {
+                {
+                    const int c = tid;
                     int f = c < ncols ? __ldg(ip + c) : 0;
                     f = f < 0 ? 0 : (f >= P.F ? P.F - 1 : f);
                     s_idx[buf][c] = f;
                     s_bias[buf][c] = __bfloat162float(P.bias[f]);
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, NUM_EPI);
             }
-            mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
-            tc_fence_after_sync();
             const uint32_t tacc = tm + buf * BN + lane_off;
-            if (!IS_MM2) {
+            if (P.dbg & 8) {
+                mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
+            } else if (!IS_MM2) {
                 __nv_bfloat16* crow = P.out + (int64_t)m * P.F + nb * BN;
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tacc + c0, r);
-                    // cached activations of these 32 neurons for this token (coalesced across the warp)
-                    __nv_bfloat16 pa[32];
+                const unsigned short* pa_base = reinterpret_cast<const unsigned short*>(P.pa_T) + m;
+                // cached activations of the chunk's 32 neurons for this token: coalesced across the warp,
+                // fetched one chunk ahead (the first chunk before the accumulator is even ready)
+                unsigned short pa_cur[32], pa_nxt[32];
+                auto load_pa = [&](int c0, unsigned short (&dst)[32]) {
 #pragma unroll
                     for (int j = 0; j < 32; j++)
-                        pa[j] = (c0 + j < ncols) ? P.pa_T[(int64_t)s_idx[buf][c0 + j] * P.M + m] : __float2bfloat16(0.f);
+                        dst[j] = (c0 + j < cend) ? __ldg(pa_base + (int64_t)s_idx[buf][c0 + j] * P.M) : (unsigned short)0;
+                };
+                if (cbeg < cend) load_pa(cbeg, pa_nxt);
+                mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
+                tc_fence_after_sync();
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tacc + c0, r);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) pa_cur[j] = pa_nxt[j];
+                    if (c0 + 32 < cend) load_pa(c0 + 32, pa_nxt);
                     tmem_ld_wait();
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float g0 = gelu_tanh(__uint_as_float(r[j]) + s_bias[buf][c0 + j]) - __bfloat162float(pa[j]);
-                        const float g1 = gelu_tanh(__uint_as_float(r[j + 1]) + s_bias[buf][c0 + j + 1]) - __bfloat162float(pa[j + 1]);
+                        const float p0 = __uint_as_float((uint32_t)pa_cur[j] << 16), p1 = __uint_as_float((uint32_t)pa_cur[j + 1] << 16);
+                        const float g0 = gelu_tanh(__uint_as_float(r[j]) + s_bias[buf][c0 + j]) - p0;
+                        const float g1 = gelu_tanh(__uint_as_float(r[j + 1]) + s_bias[buf][c0 + j + 1]) - p1;
                         pk[j >> 1] = pack_bf16x2(g0, g1);
                     }
                     if (P.update_pa) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            if (c0 + j < ncols) {
+                            if (c0 + j < cend) {
                                 const float d = (j & 1) ? bf16_hi(pk[j >> 1]) : bf16_lo(pk[j >> 1]);
-                                P.pa_T[(int64_t)s_idx[buf][c0 + j] * P.M + m] = __float2bfloat16(__bfloat162float(pa[j]) + d);
+                                const float old = __uint_as_float((uint32_t)pa_cur[j] << 16);
+                                P.pa_T[(int64_t)s_idx[buf][c0 + j] * P.M + m] = __float2bfloat16(old + d);
                             }
                         }
                     }
-                    const int nvalid = min(32, ncols - c0);     // multiple of 16
+                    const int nvalid = min(32, cend - c0);     // multiple of 16
 #pragma unroll
                     for (int q4 = 0; q4 < 4; q4++)
-                        if (q4 * 8 < nvalid)
+                        if (q4 * 8 < nvalid && !(P.dbg & 16))
                             *reinterpret_cast<uint4*>(crow + c0 + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
                 }
             } else {
                 __nv_bfloat16* orow = P.out + (int64_t)m * P.N + nb * BN;
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint4 old_nxt[4], old[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) old_nxt[q4] = *reinterpret_cast<const uint4*>(orow + cbeg + q4 * 8);
+                mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
+                tc_fence_after_sync();
+                for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(tacc + c0, r);
-                    uint4 old[4];
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) old[q4] = *reinterpret_cast<const uint4*>(orow + c0 + q4 * 8);
+                    for (int q4 = 0; q4 < 4; q4++) old[q4] = old_nxt[q4];
+                    if (c0 + 32 < cbeg + BN / 2) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; q4++) old_nxt[q4] = *reinterpret_cast<const uint4*>(orow + c0 + 32 + q4 * 8);
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int q4 = 0; q4 < 4; q4++) {
@@ -305,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                             const uint32_t a = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]), __uint_as_float(r[q4 * 8 + 2 * j + 1]));
                             w[j] = pack_bf16x2(bf16_lo(a) + bf16_lo(ov[j]), bf16_hi(a) + bf16_hi(ov[j]));
                         }
-                        *reinterpret_cast<uint4*>(orow + c0 + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        if (!(P.dbg & 16)) *reinterpret_cast<uint4*>(orow + c0 + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -314,7 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
             tcount++;
         }
     } else {
-        setmaxnreg_dec<96>();     // warps 6-7: idle, setmaxnreg is warpgroup-wide
+        setmaxnreg_dec<88>();     // warps 14-15: idle, setmaxnreg is warpgroup-wide
     }
 
     tc_fence_before_sync();
@@ -379,13 +409,13 @@ static int launch_mlp(const CUtensorMap& tmap, Params& P, cudaStream_t stream) {
     static bool configured = false;
     auto kern = mlp_kernel<IS_MM2>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IS_MM2 ? SMEM_MM2 : SMEM_MM1);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int tiles = P.n_mb * P.n_nb;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap, P);
+    kern<<<grid, NUM_THREADS, IS_MM2 ? SMEM_MM2 : SMEM_MM1, stream>>>(tmap, P);
     return (int)cudaGetLastError();
 }
 
@@ -404,6 +434,7 @@ extern "C" int cm_csp_mlp_mm1(const void* a, const void* w1, void* c, const void
     P.pa_T = (__nv_bfloat16*)pa_T; P.indices = indices; P.counts = counts;
     P.M = M; P.K = K; P.F = F; P.N = F; P.idx_stride = idx_stride; P.update_pa = update_pa ? 1 : 0;
     P.n_mb = M / BM; P.n_nb = (F + BN - 1) / BN;
+    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
     return launch_mlp<false>(tmap, P, (cudaStream_t)stream);
 }
 
@@ -437,5 +468,6 @@ extern "C" int cm_csp_mlp_mm2(const void* packed, const void* w2_T, void* out, v
     P.indices = indices; P.counts = counts;
     P.M = M; P.K = F; P.F = F; P.N = N; P.idx_stride = idx_stride; P.update_pa = 0;
     P.n_mb = M / BM; P.n_nb = N / BN;
+    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
     return launch_mlp<true>(tmap, P, (cudaStream_t)stream);
 }

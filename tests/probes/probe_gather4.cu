@@ -52,13 +52,13 @@ __global__ void layout_probe(const __grid_constant__ CUtensorMap map, const int*
 }
 
 constexpr int TILE_ROWS = 128;
-template <int MODE>   // 0: cp.async, 1: gather4 from 1 thread, 4: gather4 from 4 threads
+template <int MODE>   // 0: cp.async, 1: gather4 from 1 thread, 4: gather4 from 4 threads, 5: two 2-D TMA tile loads (64 cols x 128 rows)
 __global__ void __launch_bounds__(160) bw_probe(const __grid_constant__ CUtensorMap map, const __nv_bfloat16* mat,
                                                 const int* rows, int nrows_list, int iters, unsigned long long* cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full[4];
     const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
-    if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) mbar_init(&full[i], MODE == 0 ? 128 : (MODE == 1 ? 1 : 4)); fence_mbar_init(); }
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) mbar_init(&full[i], (MODE == 0 || MODE == 6 || MODE == 7) ? 128 : (MODE == 4 ? 4 : 1)); fence_mbar_init(); }
     __syncthreads();
     const int tid = threadIdx.x;
     unsigned long long t0 = clock64();
@@ -78,6 +78,54 @@ __global__ void __launch_bounds__(160) bw_probe(const __grid_constant__ CUtensor
                     cp_async_16(dst + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), src);
                 }
                 cp_async_mbar_arrive_noinc(&full[slot]);
+            } else if (MODE == 6 || MODE == 7) {
+                // 6: all 16 loads of a thread in flight, then 16 stores; 7: same but 256-bit loads (8 per thread)
+                const int chunk = pt & 15, rsub = pt >> 4;
+                if (MODE == 6) {
+                    uint4 v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int r = rsub + 8 * i;
+                        v[i] = __ldg(reinterpret_cast<const uint4*>(mat + (size_t)rl[r] * 128 + chunk * 8));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int r = rsub + 8 * i;
+                        uint32_t a = dst + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w) : "memory");
+                    }
+                } else {
+                    const int c32 = pt & 7, rs = pt >> 3;      // 8 x 32-byte pieces per row, 16 rows per pass
+                    uint32_t v[8][8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        int r = rs + 16 * i;
+                        const void* src = mat + (size_t)rl[r] * 128 + c32 * 16;
+                        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                                     : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]), "=r"(v[i][4]), "=r"(v[i][5]), "=r"(v[i][6]), "=r"(v[i][7]) : "l"(src));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        int r = rs + 16 * i;
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {
+                            int chunk = c32 * 2 + hh;
+                            uint32_t a = dst + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(v[i][4*hh]), "r"(v[i][4*hh+1]), "r"(v[i][4*hh+2]), "r"(v[i][4*hh+3]) : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&full[slot]);
+            } else if (MODE == 5) {
+                if (pt == 0) {
+                    mbar_arrive_expect_tx(&full[slot], 32768);
+                    const int row0 = (rl[0] & ~127);
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::1 [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(dst), "l"(&map), "r"(0), "r"(row0), "r"(smem_u32(&full[slot])) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::1 [%0], [%1, {%2, %3}], [%4];\n"
+                                 ::"r"(dst + 16384), "l"(&map), "r"(64), "r"(row0), "r"(smem_u32(&full[slot])) : "memory");
+                }
             } else {
                 const int nthr = MODE == 1 ? 1 : 4;
                 if (pt < nthr) {
@@ -93,7 +141,7 @@ __global__ void __launch_bounds__(160) bw_probe(const __grid_constant__ CUtensor
         if (MODE == 0) cp_async_wait_all();
     }
     __syncthreads();
-    if (MODE != 0 && tid == 32) {   // wait for the final fills
+    if (MODE != 0 && MODE != 6 && MODE != 7 && tid == 32) {   // wait for the final fills
         for (int it = max(0, iters - 4); it < iters; it++) mbar_wait(&full[it & 3], (it >> 2) & 1);
     }
     __syncthreads();
@@ -146,25 +194,32 @@ int main() {
     int* drl; CK(cudaMalloc(&drl, NL * 4)); CK(cudaMemcpy(drl, rl.data(), NL * 4, cudaMemcpyHostToDevice));
     unsigned long long* dcy; CK(cudaMalloc(&dcy, 148 * 8));
     const int iters = 2000;
-    auto run = [&](auto kern, const char* name) {
+    auto run = [&](auto kern, const char* name, const CUtensorMap& map, int grid) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 1024));
-        kern<<<148, 160, 4 * 32768 + 1024>>>(map, d, drl, NL, iters, dcy);
+        kern<<<grid, 160, 4 * 32768 + 1024>>>(map, d, drl, NL, iters, dcy);
         CK(cudaDeviceSynchronize());
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        kern<<<148, 160, 4 * 32768 + 1024>>>(map, d, drl, NL, iters, dcy);
+        kern<<<grid, 160, 4 * 32768 + 1024>>>(map, d, drl, NL, iters, dcy);
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
-        std::vector<unsigned long long> cy(148);
-        CK(cudaMemcpy(cy.data(), dcy, 148 * 8, cudaMemcpyDeviceToHost));
-        double avg = 0; for (auto c : cy) avg += c; avg /= 148;
-        double bytes = (double)iters * 32768 * 148;
-        printf("%-28s %.3f ms  %.0f GB/s aggregate  %.1f B/clk/SM  (%.0f cycles per 32 KB tile)\n", name, ms, bytes / ms / 1e6,
+        std::vector<unsigned long long> cy(grid);
+        CK(cudaMemcpy(cy.data(), dcy, grid * 8, cudaMemcpyDeviceToHost));
+        double avg = 0; for (auto c : cy) avg += c; avg /= grid;
+        double bytes = (double)iters * 32768 * grid;
+        printf("%-28s grid=%3d %.3f ms  %.0f GB/s aggregate  %.1f B/clk/SM  (%.0f cycles per 32 KB tile)\n", name, grid, ms, bytes / ms / 1e6,
                (double)iters * 32768 / avg, avg / iters);
     };
-    run(bw_probe<0>, "cp.async 16B x128 threads");
-    run(bw_probe<1>, "gather4 x1 thread");
-    run(bw_probe<4>, "gather4 x4 threads");
+    CUtensorMap map_tile;
+    cuuint32_t box_tile[2] = {64, 128};
+    encode(&map_tile, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, gdim, gstr, box_tile, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    for (int grid : {8, 37, 74, 148}) run(bw_probe<0>, "cp.async 16B x128 threads", map, grid);
+    for (int grid : {8, 148}) run(bw_probe<6>, "LDG.128 -> STS.128 x128 thr", map, grid);
+    for (int grid : {8, 148}) run(bw_probe<7>, "LDG.256 -> STS.128 x128 thr", map, grid);
+    for (int grid : {8, 37, 74, 148}) run(bw_probe<5>, "TMA 2-D tiles 2 x 16 KB", map_tile, grid);
+    run(bw_probe<1>, "gather4 x1 thread", map, 148);
+    run(bw_probe<4>, "gather4 x4 threads", map, 148);
     return 0;
 }
