@@ -1,0 +1,58 @@
+"""Single-node multi-GPU plumbing for the sparse-delta path: one process per GPU, heads (attention)
+or 128-token blocks (MLP) sharded across ranks, and ONE all-gather of the attention output per layer.
+
+This replaces the reference's HunyuanVideo head-parallel path -- two `all_to_all_single` per attention
+plus an `all_gather_into_tensor` of the text tokens (examples/hunyuan/hyvideo/modules/head_parallel.py:
+36-115, attenion.py:229-292) -- for the case where every rank already holds q/k/v of its heads:
+index/mask tensors are per head, so they shard with the heads and never move.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_units: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of `n_units` for `rank`; the first n_units % world ranks get one more."""
+    base, extra = divmod(n_units, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_heads(num_heads: int, world: int, rank: int) -> Tuple[int, int]:
+    """The reference requires heads % world == 0 (`local_heads_num = heads // world_size`, models.py:749);
+    here uneven splits are allowed and the gather pads to the largest shard."""
+    return shard_range(num_heads, world, rank)
+
+
+def all_gather_heads(o_local: torch.Tensor, num_heads: int, group=None) -> torch.Tensor:
+    """o_local [B, h_local, N, D] on every rank  ->  [B, num_heads, N, D] on every rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return o_local
+    B, h_local, N, D = o_local.shape
+    h_max = -(-num_heads // world)
+    if num_heads % world == 0:
+        out = o_local.new_empty(world * B, h_local, N, D)        # rank-major concatenation along dim 0
+        dist.all_gather_into_tensor(out, o_local.contiguous(), group=group)
+        return out.view(world, B, h_local, N, D).permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
+    padded = o_local.new_zeros(B, h_max, N, D)
+    padded[:, :h_local] = o_local
+    out = o_local.new_empty(world * B, h_max, N, D)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    out = out.view(world, B, h_max, N, D)
+    parts = []
+    for r in range(world):
+        b, e = shard_heads(num_heads, world, r)
+        parts.append(out[r, :, : e - b])
+    return torch.cat(parts, dim=1)
+
+
+def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
+    """One sparse attention step with heads sharded over the ranks of `group`.
+    q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output."""
+    o = o_cache.clone()
+    torch.ops.chipmunk.csp_attn(q, k, v, o, indices, counts, 1)
+    return all_gather_heads(o, num_heads, group)
