@@ -351,11 +351,11 @@ def c3_attention(dev, world, rank):
                     "gather_gbs": round(attn_alg_bytes(H, n, count) / t / 1e6, 1)})
         return res
     import torch.distributed as dist
-    full = torch.empty(world, hl, n, D, device=dev, dtype=bf)
+    from chipmunk_b200 import parallel
 
     def layer():
-        torch.ops.chipmunk.csp_attn(q, k, v, o, idx, cnt, 1)
-        dist.all_gather_into_tensor(full, o[0])
+        # cache clone + csp_attn on this rank's heads + ONE all-gather of O
+        return parallel.sparse_attention_head_parallel(q, k, v, o, idx, cnt, hl * world)
 
     for _ in range(2):
         layer()

@@ -27,13 +27,11 @@
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace cm {
 namespace attn {
 
-constexpr int D = 128;              // head dim
-constexpr int QG = 192;             // query rows per tile
-constexpr int KT = 128;             // key columns per step
 constexpr int NSLOT = 5;            // 32 KB K/V slots
 constexpr int SLOT_BYTES = KT * D * 2;
 constexpr int Q_HALF_BYTES = QG * 128;          // one 64-wide d-half of the Q tile
@@ -47,8 +45,6 @@ constexpr int NUM_PROD = 128;
 
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 384;
 
-constexpr float SCALE_LOG2 = 0.08838834764f * 1.44269504089f;   // log2(e)/sqrt(128)
-constexpr float RESCALE_THRESHOLD = 8.0f;                        // in log2 units
 
 struct Params {
     const __nv_bfloat16* q;
@@ -78,79 +74,6 @@ __device__ __forceinline__ int tile_count(const Params& P, int tile, bool dense)
     int c = __ldg(P.counts + tile);
     c = c < 0 ? 0 : c;
     return c > (int)P.idx_row_stride ? (int)P.idx_row_stride : c;
-}
-
-// One softmax step of one query row (= one thread): S row (128 fp32 in TMEM) -> P row (bf16, written
-// over the first 64 columns of S).  m_ref is the row's reference maximum in raw score units; it is
-// only moved (and O / l rescaled) when the new tile maximum exceeds it by more than 2^8 after
-// scaling, so most steps skip the correction.  TAIL masks packed positions >= valid by position
-// (reference csp_attn.cu:272) by loading them as -inf.
-template <bool TAIL>
-__device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref,
-                                             float& l_sum) {
-    uint32_t s[KT];
-#pragma unroll
-    for (int c = 0; c < KT; c += 32) tmem_ld32(tS + c, s + c);
-    tmem_ld_wait();
-    if (TAIL) {
-#pragma unroll
-        for (int j = 0; j < KT; j++) s[j] = j < valid ? s[j] : 0xff800000u;
-    }
-    // ---- tile max: 4 independent chains of 3-input max
-    float mx[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        mx[c] = __uint_as_float(s[c * 32]);
-#pragma unroll
-        for (int j = 1; j < 31; j += 2)
-            mx[c] = fmax3(mx[c], __uint_as_float(s[c * 32 + j]), __uint_as_float(s[c * 32 + j + 1]));
-        mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 32 + 31]));
-    }
-    const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-    // ---- lazy rescale of the running state (always taken on the first step: m_ref = -inf)
-    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
-    if (__any_sync(0xffffffffu, need)) {
-        float alpha = 1.f;
-        if (need) {
-            alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);
-            m_ref = m_tile;
-            l_sum *= alpha;
-        }
-        if (kk > 0) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tO + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-                tmem_st_32x32b_x32(tO + c0, r);
-            }
-        }
-    }
-    // ---- P = exp2(s*c - m*c) (packed fp32x2 FMA), row sum, bf16 pack, write over S
-    const float neg_m = -m_ref * SCALE_LOG2;
-    const uint64_t c2 = pack_f32x2(SCALE_LOG2, SCALE_LOG2), nm2 = pack_f32x2(neg_m, neg_m);
-    uint64_t acc[2] = {0ull, 0ull};
-    const int cols = TAIL ? ((valid + 15) & ~15) : KT;
-#pragma unroll
-    for (int c0 = 0; c0 < KT; c0 += 32) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const uint64_t x = ffma2(pack_f32x2(__uint_as_float(s[c0 + j]), __uint_as_float(s[c0 + j + 1])), c2, nm2);
-            float x0, x1;
-            unpack_f32x2(x, x0, x1);
-            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-            acc[(j >> 1) & 1] = fadd2(acc[(j >> 1) & 1], pack_f32x2(p0, p1));
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-        }
-        if (!TAIL || c0 < cols) tmem_st_32x32b_x16(tS + (c0 >> 1), pk);
-    }
-    float a0, a1, a2, a3;
-    unpack_f32x2(acc[0], a0, a1);
-    unpack_f32x2(acc[1], a2, a3);
-    l_sum += (a0 + a1) + (a2 + a3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -434,6 +357,12 @@ static int launch_attn(Params& P, cudaStream_t stream) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool strides_ok(const int64_t s[3]) { return s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0; }
 
+namespace cm { namespace attn2 {
+int launch(const void* q, const void* k, const void* v, void* o, const int32_t* indices, const int32_t* counts, int B,
+           int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
+           int64_t idx_row_stride, int o_scale, int accumulate, cudaStream_t stream);
+} }
+
 extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,
                            const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
                            const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
@@ -446,6 +375,11 @@ extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
     if (!strides_ok(q_strides) || !strides_ok(k_strides) || !strides_ok(v_strides) || !strides_ok(o_strides))
         return CM_EALIGN;
     if (!is_sm100()) return CM_EARCH;
+    // CM_ATTN_V2=1 selects the experimental CTA-pair kernel (csp_attn2.cu: correct, not yet faster)
+    static const bool use_v2 = getenv("CM_ATTN_V2") && atoi(getenv("CM_ATTN_V2")) != 0;
+    if (use_v2)
+        return cm::attn2::launch(q, k, v, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
+                                 idx_row_stride, o_scale, accumulate, (cudaStream_t)stream);
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
     P.o = (__nv_bfloat16*)o;
