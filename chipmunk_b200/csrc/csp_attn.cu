@@ -179,28 +179,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         setmaxnreg_inc<208>();
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
         const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
+        const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
+        const uint64_t desc_k = umma_smem_desc(sKV, 16, 1024);                   // K-major B: gathered K rows
+        const uint64_t desc_v = umma_smem_desc(sKV, SLOT_BYTES / 2, 1024);       // MN-major B: gathered V rows
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
             const int count = tile_count(P, tile, DENSE);
             if (count <= 0) { it--; continue; }
             const int nk = (count + KT - 1) / KT;
             auto ncols = [&](int kk) { int v = count - kk * KT; v = v > KT ? KT : v; return (v + 15) & ~15; };
 
+            // The issuing thread is the kernel's scarcest resource: descriptors are built once (their fields
+            // are constant but for the 14-bit start address) and each MMA only adds a compile-time offset.
             auto issue_S = [&](int blk, uint32_t slot, int cols) {
                 const uint32_t idesc = umma_idesc_bf16(128, cols, 0, 0);
                 const uint32_t d = tm + (blk ? TM_S1 : TM_S0);
+                const uint64_t ad0 = desc_q + (uint64_t)(blk * ((128 * 128) >> 4));
+                const uint64_t bd0 = desc_k + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                if (P.dbg & 2) return;
 #pragma unroll
-                for (int k16 = 0; k16 < ((P.dbg & 2) ? 0 : D / 16); k16++) {
-                    uint64_t ad = umma_smem_desc(sQ + (k16 >> 2) * Q_HALF_BYTES + blk * (128 * 128) + (k16 & 3) * 32, 16, 1024);
-                    uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + (k16 >> 2) * (SLOT_BYTES / 2) + (k16 & 3) * 32, 16, 1024);
+                for (int k16 = 0; k16 < D / 16; k16++) {
+                    const uint64_t ad = ad0 + (uint64_t)((((k16 >> 2) * Q_HALF_BYTES) + (k16 & 3) * 32) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)((((k16 >> 2) * (SLOT_BYTES / 2)) + (k16 & 3) * 32) >> 4);
                     umma_ss(d, ad, bd, idesc, k16 > 0);
                 }
             };
             auto issue_PV = [&](int blk, uint32_t slot, int cols, bool first) {
                 const uint32_t d = tm + (blk ? TM_O1 : TM_O0);
                 const uint32_t a = tm + (blk ? TM_S1 : TM_S0);
-                for (int j = 0; j < ((P.dbg & 2) ? 0 : cols / 16); j++) {
-                    uint64_t bd = umma_smem_desc(sKV + slot * SLOT_BYTES + j * 2048, SLOT_BYTES / 2, 1024);
-                    umma_ts(d, a + j * 8, bd, idesc_pv, (!first) || j > 0);
+                const uint64_t bd0 = desc_v + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                if (P.dbg & 2) return;
+                if (cols == KT) {
+#pragma unroll
+                    for (int j = 0; j < KT / 16; j++) umma_ts(d, a + j * 8, bd0 + (uint64_t)(j * (2048 >> 4)), idesc_pv, (!first) || j > 0);
+                } else {
+                    for (int j = 0; j < cols / 16; j++) umma_ts(d, a + j * 8, bd0 + (uint64_t)(j * (2048 >> 4)), idesc_pv, (!first) || j > 0);
                 }
             };
 
@@ -308,14 +320,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                         for (int j = 0; j < 4; j++)
                             w[j] = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]) * inv, __uint_as_float(r[q4 * 8 + 2 * j + 1]) * inv);
                         uint4* dst = reinterpret_cast<uint4*>(orow + c0 + q4 * 8);
-                        if (P.accumulate) {
-                            uint4 old = *dst;
-                            uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                w[j] = pack_bf16x2(bf16_lo(ov[j]) + bf16_lo(w[j]), bf16_hi(ov[j]) + bf16_hi(w[j]));
-                        }
-                        *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                        // the delta add-back: o = bf16(o + delta) as a 16-byte reduction at the L2 (the reference
+                        // uses a TMA reduce-add, csp_attn.cu:300); plain store for csp_128_attn / dense
+                        if (P.accumulate) red_add_bf16x8(dst, w[0], w[1], w[2], w[3]);
+                        else *dst = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }

@@ -363,14 +363,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) attn
                         for (int j = 0; j < 4; j++)
                             w[j] = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]) * inv, __uint_as_float(r[q4 * 8 + 2 * j + 1]) * inv);
                         uint4* dst = reinterpret_cast<uint4*>(orow + c0 + q4 * 8);
-                        if (P.accumulate) {
-                            const uint4 old = *dst;
-                            const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                w[j] = pack_bf16x2(bf16_lo(ov[j]) + bf16_lo(w[j]), bf16_hi(ov[j]) + bf16_hi(w[j]));
-                        }
-                        *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                        // the delta add-back: o = bf16(o + delta) as a 16-byte reduction at the L2 (the reference
+                        // uses a TMA reduce-add, csp_attn.cu:300); plain store for csp_128_attn / dense
+                        if (P.accumulate) red_add_bf16x8(dst, w[0], w[1], w[2], w[3]);
+                        else *dst = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }

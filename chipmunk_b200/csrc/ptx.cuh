@@ -54,10 +54,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+#ifdef CM_SPIN_WAIT
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_test_wait(bar, parity)) {
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+#endif
 
 // ---------------------------------------------------------------- proxies / fences
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
@@ -108,6 +126,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 // 1-D bulk copy shared -> global.
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+                 "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+// 16-byte vector reduction: dst[0..7] = bf16(dst + v) per element, performed at the L2 (REDG.ADD.BF16x8.RN).
+// Fire-and-forget: no load latency on the issuing thread.
+__device__ __forceinline__ void red_add_bf16x8(void* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 1-D bulk reduction shared -> global: dst[i] = bf16(dst[i] + src[i]) performed at the L2 (noftz bf16 add).
+__device__ __forceinline__ void bulk_reduce_add_bf16_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;\n" ::"l"(dst),
                  "r"(src_smem), "r"(bytes)
                  : "memory");
 }
