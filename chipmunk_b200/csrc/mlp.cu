@@ -162,20 +162,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                     int f = pos < cnt_all ? __ldg(ip + pos) : -1;
                     return f >= P.F ? P.F - 1 : f;
                 };
-                int f_next = fetch(0);
-                for (int ks = 0; ks < ksteps; ks++, it++) {
-                    const int f_cur = f_next;
-                    if (ks + 1 < ksteps) f_next = fetch(ks + 1);
-                    const uint32_t s = it % STAGES;
-                    mbar_wait(&bar.empty[s], ((it / STAGES) & 1) ^ 1);
-                    const uint32_t dst = sbase + s * STAGE_BYTES + A_BYTES + dcol;
+                // index loads run IDX_AHEAD stages ahead of their use (statically rotated registers): a stage
+                // (~0.5 us) is shorter than a global-load round trip
+                constexpr int IDX_AHEAD = 4;
+                int fq[IDX_AHEAD];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int r = w + 4 * i;
-                        const int f = __shfl_sync(0xffffffffu, f_cur, i);
-                        if (f >= 0 && !(P.dbg & 1)) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
+                for (int j = 0; j < IDX_AHEAD; j++) fq[j] = j < ksteps ? fetch(j) : -1;
+                for (int ks0 = 0; ks0 < ksteps; ks0 += IDX_AHEAD) {
+#pragma unroll
+                    for (int j = 0; j < IDX_AHEAD; j++) {
+                        const int ks = ks0 + j;
+                        if (ks >= ksteps) break;
+                        const int f_cur = fq[j];
+                        if (ks + IDX_AHEAD < ksteps) fq[j] = fetch(ks + IDX_AHEAD);
+                        const uint32_t s = it % STAGES;
+                        mbar_wait(&bar.empty[s], ((it / STAGES) & 1) ^ 1);
+                        const uint32_t dst = sbase + s * STAGE_BYTES + A_BYTES + dcol;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const int r = w + 4 * i;
+                            const int f = __shfl_sync(0xffffffffu, f_cur, i);
+                            if (f >= 0 && !(P.dbg & 1)) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
+                        }
+                        cp_async_mbar_arrive_noinc(&bar.full[s]);
+                        it++;
                     }
-                    cp_async_mbar_arrive_noinc(&bar.full[s]);
                 }
             }
         }
