@@ -18,6 +18,7 @@ _alias = {
     "chipmunk.ops": ops, "chipmunk.modules": modules, "chipmunk.util": util,
     "chipmunk.ops.attn": _impl.ops.attn, "chipmunk.ops.mlp": _impl.ops.mlp,
     "chipmunk.ops.indexed_io": _impl.ops.indexed_io, "chipmunk.ops.bitpack": _impl.ops.bitpack,
+    "chipmunk.ops.patch": _impl.ops.patch, "chipmunk.ops.voxel": _impl.ops.voxel,
     "chipmunk.modules.attn": _impl.modules.attn, "chipmunk.modules.mlp": _impl.modules.mlp,
     "chipmunk.util.config": _impl.util.config, "chipmunk.util.layer_counter": _impl.util.layer_counter,
     "chipmunk.util.storage": _impl.util.storage,

@@ -1,0 +1,124 @@
+"""3-D voxel token reordering and static local masks for video DiTs
+(reference: src/chipmunk/ops/voxel.py:9-304).
+
+`voxel_chunk_no_padding` groups tokens of a [t, h, w] latent into vt x vh x vw voxels (so that a
+192-token query group is spatially compact) and appends the ragged tails in raster order; like the
+2-D patching it is a fixed permutation, built once per shape and applied with one gather.
+"""
+from __future__ import annotations
+
+from functools import lru_cache
+
+import torch
+
+
+@lru_cache(maxsize=16)
+def _voxel_perm(t: int, h: int, w: int, vt: int, vh: int, vw: int, device: str):
+    dev = torch.device(device)
+    T, H, W = (t // vt) * vt, (h // vh) * vh, (w // vw) * vw
+    tt = torch.arange(t, device=dev)[:, None, None].expand(t, h, w)
+    hh = torch.arange(h, device=dev)[None, :, None].expand(t, h, w)
+    ww = torch.arange(w, device=dev)[None, None, :].expand(t, h, w)
+    src = (tt * h + hh) * w + ww
+    main = (tt < T) & (hh < H) & (ww < W)
+    nh, nw = H // vh if vh else 0, W // vw if vw else 0
+    key_main = ((((tt // vt) * nh + hh // vh) * nw + ww // vw) * vt + tt % vt) * (vh * vw) + (hh % vh) * vw + ww % vw
+    order = [src[main][key_main[main].argsort()]]
+    # tails, each in raster order: t >= T (all h, w); then t < T, h >= H (all w); then t < T, h < H, w >= W
+    order.append(src[tt >= T])
+    order.append(src[(tt < T) & (hh >= H)])
+    order.append(src[(tt < T) & (hh < H) & (ww >= W)])
+    perm = torch.cat([o.reshape(-1) for o in order])
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel(), device=dev)
+    return perm, inv
+
+
+def voxel_chunk_no_padding(x: torch.Tensor, voxel_shape=(4, 4, 4)) -> torch.Tensor:
+    """x [b, ah, t, h, w, d] -> [b, ah, t*h*w, d] in voxel order (tails appended)."""
+    b, ah, t, h, w, d = x.shape
+    perm, _ = _voxel_perm(t, h, w, *voxel_shape, str(x.device))
+    return x.reshape(b, ah, t * h * w, d).index_select(2, perm)
+
+
+def reverse_voxel_chunk_no_padding(x_chunk_flat: torch.Tensor, original_shape, voxel_shape=(4, 4, 4)) -> torch.Tensor:
+    b, ah, t, h, w, d = original_shape
+    _, inv = _voxel_perm(t, h, w, *voxel_shape, str(x_chunk_flat.device))
+    return x_chunk_flat.index_select(2, inv).reshape(b, ah, t, h, w, d)
+
+
+def masktoinds(mask: torch.Tensor, multiple=None):
+    """Pure-torch statement of mask -> (indices, counts): set columns first (reference voxel.py:161-180)."""
+    counts = mask.sum(dim=-1).to(torch.int32)
+    if multiple is not None:
+        counts = ((counts + multiple - 1) // multiple) * multiple
+    inds = mask.to(torch.int8).argsort(dim=-1, descending=True, stable=True)
+    return inds.contiguous().to(torch.int32), counts.contiguous()
+
+
+def _axis_window(n: int, reach: int, device) -> torch.Tensor:
+    """[n, n] bool: window[i, j] = j is one of the 2*reach+1 positions around i, shifted inward at the
+    borders so that every position sees exactly 2*reach+1 neighbours (reference `offsets`, voxel.py:101-113)."""
+    i = torch.arange(n, device=device)
+    lo = (i - reach).clamp(min=0)
+    lo = torch.minimum(lo, torch.tensor(max(n - (2 * reach + 1), 0), device=device))
+    j = torch.arange(n, device=device)
+    return (j[None, :] >= lo[:, None]) & (j[None, :] < (lo + 2 * reach + 1)[:, None])
+
+
+def get_local_voxel_mask(full_shape, local_shape, device) -> torch.Tensor:
+    """[t*h*w, t*h*w] bool: voxel b attends voxel a iff a lies in the (lt+1 x lh+1 x lw+1) box around b
+    (the index list the reference builds with a 6-deep Python loop, voxel.py:115-158)."""
+    t, h, w = full_shape
+    lt, lh, lw = local_shape
+    n = t * h * w
+    if lt == 0 or lh == 0 or lw == 0:
+        m = torch.zeros(n, n, dtype=torch.bool, device=device)
+        m[:, 0] = True          # the reference returns all-zero index lists, i.e. every voxel "sees" voxel 0
+        return m
+    wt, wh, ww = _axis_window(t, lt // 2, device), _axis_window(h, lh // 2, device), _axis_window(w, lw // 2, device)
+    m = (wt[:, None, None, :, None, None] & wh[None, :, None, None, :, None] & ww[None, None, :, None, None, :]).reshape(n, n)
+    if (lt % 2) or (lh % 2) or (lw % 2):
+        m = m.clone()
+        m[:, 0] = True      # odd extents leave zero-initialised slots in the reference's index table -> voxel 0
+    return m
+
+
+def get_local_indices_with_text(vid_shape, txt_len, voxel_shape, local_shape, full_tail_from_attn=False,
+                                full_tail_to_attn=False, rk=0, kv_tile_size=128, device=torch.device("cuda")):
+    """Static attention mask for a video + text sequence in voxel order: every query group (one voxel of
+    vt*vh*vw tokens) attends the text tokens and its local box of voxels (reference voxel.py:206-304).
+    Returns (mask [n_groups, seq], inds, counts)."""
+    tt, th, tw = vid_shape
+    lt, lh, lw = local_shape
+    vt, vh, vw = voxel_shape
+    vid, seq = tt * th * tw, tt * th * tw + txt_len
+    vsize = vt * vh * vw
+    n_groups = (seq + vsize - 1) // vsize
+    mask = torch.zeros(n_groups, seq, dtype=torch.bool, device=device)
+    mask[:, vid:] = True
+    gt, gh, gw = tt // vt, th // vh, tw // vw
+    n_img = gt * gh * gw
+    local = get_local_voxel_mask((gt, gh, gw), (lt, lh, lw), device)               # [n_img, n_img] voxels
+    local = local[:, :, None].expand(n_img, n_img, vsize).reshape(n_img, n_img * vsize)[:n_groups, :seq]
+    rows, cols = local.shape
+    mask[:rows, :cols] |= local
+    pad0, pad1 = n_groups - n_img, seq - cols
+    if pad1 > 0 and full_tail_to_attn:
+        mask[:rows, cols:] = True
+    local_size = vsize * lt * lh * lw
+    if local_size > 0 and pad0 > 0:
+        mask[n_groups - pad0:, seq - local_size:] = True
+    tail_cols = (seq // kv_tile_size) * kv_tile_size
+    txt_rows = txt_len // vsize + 1
+    mask[n_groups - txt_rows:, seq - tail_cols:] = True
+    if full_tail_from_attn and pad0 > 0:
+        mask[n_groups - pad0:, seq - tail_cols:] = True
+    if rk > 0:
+        rand = torch.rand(mask.shape, device=device) < rk
+        if full_tail_from_attn and pad0 > 0:
+            rand[n_groups - pad0:] = False
+        rand[n_groups - txt_rows:] = False
+        mask |= rand
+    inds, counts = masktoinds(mask, multiple=kv_tile_size)
+    return mask, inds, counts

@@ -70,6 +70,28 @@ def main():
         cases[f"counts{i}"] = counts.numpy()      # nnz rounded up to `mult`
         cases[f"nnz{i}"] = nnz.numpy()
     np.savez_compressed(os.path.join(HERE, "masktoinds.npz"), **cases)
+    # ---- token reordering (ops/patch.py, ops/voxel.py): toy shapes incl. ragged tails
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))      # `chipmunk` alias -> chipmunk.util for patch.py
+    ref_patch = _load("patch")
+    cases = {}
+    x = torch.randn(3, 16, 24, generator=g)
+    cases["patch_x"] = x.numpy()
+    cases["patch_y"] = ref_patch.patchify(x).numpy()
+    assert torch.equal(ref_patch.unpatchify(ref_patch.patchify(x), (3, 16, 24)), x)
+    pe = torch.randn(1, 1, 5 + 16 * 24, 4, 2, 2, generator=g)
+    cases["rope_in"] = pe.numpy().copy()
+    cases["rope_out"] = ref_patch.patchify_rope((1, 16 * 24, 8), pe.clone(), 24, 16).numpy()
+    for i, (shape, vox) in enumerate([((1, 2, 8, 12, 16, 3), (4, 6, 8)), ((1, 1, 9, 13, 17, 2), (4, 6, 8)), ((2, 1, 5, 4, 6, 1), (4, 4, 4))]):
+        xv = torch.randn(shape, generator=g)
+        yv = ref_voxel.voxel_chunk_no_padding(xv, voxel_shape=vox)
+        assert torch.equal(ref_voxel.reverse_voxel_chunk_no_padding(yv, shape, voxel_shape=vox), xv)
+        cases[f"vox_x{i}"] = xv.numpy(); cases[f"vox_y{i}"] = yv.numpy(); cases[f"vox_shape{i}"] = np.array(vox)
+    for i, (vid, txt, local) in enumerate([((12, 18, 24), 40, (2, 2, 2)), ((16, 24, 32), 200, (0, 0, 0)), ((13, 19, 25), 70, (2, 2, 2)), ((16, 24, 32), 256, (3, 3, 3))]):
+        mask, inds, counts = ref_voxel.get_local_indices_with_text(vid, txt, (4, 6, 8), local, rk=0, kv_tile_size=128,
+                                                                   device=torch.device("cpu"))
+        cases[f"lm_args{i}"] = np.array(list(vid) + [txt] + list(local))
+        cases[f"lm_mask{i}"] = mask.numpy(); cases[f"lm_counts{i}"] = counts.numpy()
+    np.savez_compressed(os.path.join(HERE, "reorder.npz"), **cases)
     print("wrote", sorted(os.listdir(HERE)))
 
 
