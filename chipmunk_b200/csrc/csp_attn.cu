@@ -371,6 +371,12 @@ int launch(const void* q, const void* k, const void* v, void* o, const int32_t* 
            int64_t idx_row_stride, int o_scale, int accumulate, cudaStream_t stream);
 } }
 
+namespace cm { namespace attn3 {
+int launch(const void* q, const void* k, const void* v, void* o, float* l, const int32_t* indices, const int32_t* counts,
+           int B, int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
+           int64_t idx_row_stride, int o_scale, int accumulate, int dense, cudaStream_t stream);
+} }
+
 extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,
                            const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
                            const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
@@ -385,6 +391,10 @@ extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
     if (!is_sm100()) return CM_EARCH;
     // CM_ATTN_V2=1 selects the experimental CTA-pair kernel (csp_attn2.cu: correct, not yet faster)
     static const bool use_v2 = getenv("CM_ATTN_V2") && atoi(getenv("CM_ATTN_V2")) != 0;
+    static const bool use_v3 = getenv("CM_ATTN_V3") && atoi(getenv("CM_ATTN_V3")) != 0;
+    if (use_v3)
+        return cm::attn3::launch(q, k, v, o, nullptr, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
+                                 idx_row_stride, o_scale, accumulate, 0, (cudaStream_t)stream);
     if (use_v2)
         return cm::attn2::launch(q, k, v, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
                                  idx_row_stride, o_scale, accumulate, (cudaStream_t)stream);
