@@ -107,6 +107,27 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void*
                  "r"(src_bytes)
                  : "memory");
 }
+// L2 eviction-priority policies and the hinted forms of the gather / streaming loads.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async_16_zfill_hint(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst_smem), "l"(src),
+                 "r"(src_bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ int ld_nc_hint_s32(const int* p, uint64_t policy) {
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;\n" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 template <int N>

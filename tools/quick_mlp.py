@@ -3,6 +3,8 @@ import sys
 import torch
 sys.path.insert(0, ".")
 import chipmunk_b200 as cm  # noqa
+import os
+SORTED = os.environ.get("SORTED", "0") == "1"
 
 def run(M=4096, K=3072, F=12288, N=3072, count=3840, iters=10):
     dev = "cuda"
@@ -16,6 +18,8 @@ def run(M=4096, K=3072, F=12288, N=3072, count=3840, iters=10):
     pa = torch.randn(F, M, device=dev, generator=g).to(bf)
     out = torch.randn(M, N, device=dev, generator=g).to(bf)
     idx = torch.stack([torch.randperm(F, device=dev, generator=g) for _ in range(M // 128)]).int()
+    if SORTED:
+        idx[:, :count] = idx[:, :count].sort(dim=-1).values
     cnt = torch.full((M // 128,), count, dtype=torch.int32, device=dev)
     packed = torch.empty(M, F, device=dev, dtype=bf)
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -35,6 +39,8 @@ def run(M=4096, K=3072, F=12288, N=3072, count=3840, iters=10):
           f"e2e {te*1e3:.1f} us  dense cuBLAS {td*1e3:.1f} us ({dense/td/1e9:.0f} TF/s)  speedup {td/te:.2f}x", flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run(M=int(sys.argv[1]), F=int(sys.argv[2]), count=int(sys.argv[3])); sys.exit(0)
     run()
     run(count=6144)
     run(M=16384, count=3840, iters=5)
