@@ -1,6 +1,6 @@
 """chipmunk_b200 — Blackwell-native column-sparse DiT inference path.
 
-Importing the package loads libchipmunk_b200.so (built in-tree by `python -m chipmunk_b200.build`)
+Importing the package loads libchipmunk_b200.so (built in-tree by `python chipmunk_b200/build.py`)
 and registers the `torch.ops.chipmunk.*` operators.  The Python surface mirrors the reference's
 `chipmunk` package: `ops`, `modules`, `util`.
 """

@@ -21,7 +21,7 @@ def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: chipmunk_b200 has no fallback path. "
-            "Build it with `python -m chipmunk_b200.build` (needs nvcc, no GPU required).")
+            "Build it with `python chipmunk_b200/build.py` (needs nvcc, no GPU required).")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     p64 = C.POINTER(C.c_int64)

@@ -1,6 +1,6 @@
 """In-tree build of libchipmunk_b200.so (sm_100a only).
 
-    python -m chipmunk_b200.build [--force] [--verbose]
+    python chipmunk_b200/build.py [--force] [--verbose]
 
 Each `csrc/*.cu` is compiled to an object with nvcc (in parallel) and linked into
 `chipmunk_b200/libchipmunk_b200.so`.  nvcc cross-compiles without a GPU, so this also runs in
