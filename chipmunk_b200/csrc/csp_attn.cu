@@ -139,16 +139,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             // step: one coalesced-ish load per thread per step, issued one step ahead; the 16 rows a
             // thread copies are then read from its half-warp with shuffles.
             const int my_r = rsub + 8 * (lane & 15);
+            // fetch_idx returns the RAW loaded value (no arithmetic on it: that would make the warp wait for
+            // the load at the fetch and defeat the one-step-ahead prefetch); fix_idx clamps it at the use site
             auto fetch_idx = [&](int kk) -> int {
                 const int pos = kk * KT + my_r;
-                int idx = pos;
-                if (!DENSE) idx = pos < count ? __ldg(ip + pos) : 0;
+                if (DENSE) return pos;
+                return pos < count ? __ldg(ip + pos) : 0;
+            };
+            auto fix_idx = [&](int kk, int idx) -> int {
+                const int pos = kk * KT + my_r;
                 idx = idx < 0 ? 0 : (idx >= P.Nk ? P.Nk - 1 : idx);
                 return pos < count ? idx : -1;
             };
             int idx_next = fetch_idx(0);
             for (int kk = 0; kk < nk; kk++) {
-                const int idx_cur = idx_next;
+                const int idx_cur = fix_idx(kk, idx_next);
                 if (kk + 1 < nk) idx_next = fetch_idx(kk + 1);
                 int rowidx[KT / 8];
 #pragma unroll

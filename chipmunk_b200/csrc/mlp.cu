@@ -35,8 +35,9 @@ constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * 128;  // 16 KB
 constexpr int B_BYTES = BN * 128;  // 32 KB (mm1: 256 rows x 128 B; mm2: 4 n-chunks x 64 rows x 128 B)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int OUT_STAGE_BYTES = 32 * 128;            // mm2 epilogue: one 32-row x 64-column bf16 box per epilogue warp
 constexpr int SMEM_MM1 = 4 * STAGE_BYTES + 1024;
-constexpr int SMEM_MM2 = 4 * STAGE_BYTES + 1024;
+constexpr int SMEM_MM2 = 4 * STAGE_BYTES + 8 * OUT_STAGE_BYTES + 1024;
 constexpr int NUM_THREADS = 512;   // warps 0-7 epilogue (two warpgroups, 128 columns each) | 8-11 gather | 12 MMA | 13 TMA | 14-15 idle
 constexpr int WARP_MMA = 12, WARP_TMA = 13, WARP_PROD0 = 8, NUM_EPI = 256;
 
@@ -70,12 +71,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // IS_MM2 = false: mm1, IS_MM2 = true: mm2
 // ------------------------------------------------------------------------------------------
 template <bool IS_MM2>
-__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                             const __grid_constant__ CUtensorMap tmap_out, const Params P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_idx[2][BN];          // mm1 epilogue: neuron index of each packed column of the tile
-    __shared__ float s_bias[2][BN];       // mm1 epilogue: its bias
+    __shared__ int s_idx[IS_MM2 ? 1 : 2][IS_MM2 ? 1 : BN];          // mm1 epilogue: neuron index of each packed column of the tile
+    __shared__ float s_bias[IS_MM2 ? 1 : 2][IS_MM2 ? 1 : BN];       // mm1 epilogue: its bias
 
     constexpr int STAGES = 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         fence_mbar_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
-    if (warp == WARP_TMA && lane == 0) tma_prefetch_desc(&tmap_a);
+    if (warp == WARP_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); if (IS_MM2) tma_prefetch_desc(&tmap_out); }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -159,8 +161,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 auto fetch = [&](int ks) -> int {
                     const int pos = ks * BK + w + 4 * (lane & 15);
                     const int cnt_all = (ksteps - 1) * BK + klast;
-                    int f = pos < cnt_all ? __ldg(ip + pos) : -1;
-                    return f >= P.F ? P.F - 1 : f;
+                    // the raw value is returned untouched: any arithmetic on it here would make the warp wait
+                    // for the load right away and defeat the prefetch (the clamp happens at the use site)
+                    return pos < cnt_all ? __ldg(ip + pos) : -1;
                 };
                 // index loads run IDX_AHEAD stages ahead of their use (statically rotated registers): a stage
                 // (~0.5 us) is shorter than a global-load round trip
@@ -181,7 +184,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             const int r = w + 4 * i;
-                            const int f = __shfl_sync(0xffffffffu, f_cur, i);
+                            int f = __shfl_sync(0xffffffffu, f_cur, i);
+                            f = f >= P.F ? P.F - 1 : f;
                             if (f >= 0 && !(P.dbg & 1)) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
                         }
                         cp_async_mbar_arrive_noinc(&bar.full[s]);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
             const int m = mb * BM + wq * 32 + lane;
             const int cbeg = half * (BN / 2);
             const int cend = min(ncols, cbeg + BN / 2);
-            if (!IS_MM2) {
+            if constexpr (!IS_MM2) {
                 // stage this tile's neuron ids and biases (256 epilogue threads, one column each)
                 const int32_t* ip = P.indices + (int64_t)mb * P.idx_stride + nb * BN;
                 {
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
             const uint32_t tacc = tm + buf * BN + lane_off;
             if (P.dbg & 8) {
                 mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
-            } else if (!IS_MM2) {
+            } else if constexpr (!IS_MM2) {
                 __nv_bfloat16* crow = P.out + (int64_t)m * P.F + nb * BN;
                 const unsigned short* pa_base = reinterpret_cast<const unsigned short*>(P.pa_T) + m;
                 // cached activations of the chunk's 32 neurons for this token: coalesced across the warp,
@@ -320,33 +324,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                             *reinterpret_cast<uint4*>(crow + c0 + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
                 }
             } else {
-                __nv_bfloat16* orow = P.out + (int64_t)m * P.N + nb * BN;
-                uint4 old_nxt[4], old[4];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) old_nxt[q4] = *reinterpret_cast<const uint4*>(orow + cbeg + q4 * 8);
+                // O[m, tile columns] += bf16(acc): each warp packs its 32 rows x 64 columns into a 128B-swizzled
+                // 4 KB box in shared memory and ONE thread hands it to the TMA as a bf16 reduce-add on `out`
+                // (bf16(acc) first, then the bf16 add at the L2: triton/csp_mlp_mm2.py:100-101).  No global loads
+                // or stores go through the LSU, which the weight gather saturates.
+                const uint32_t stg = sbase + STAGES * STAGE_BYTES + warp * OUT_STAGE_BYTES;
                 mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
                 tc_fence_after_sync();
-                for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tacc + c0, r);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) old[q4] = old_nxt[q4];
-                    if (c0 + 32 < cbeg + BN / 2) {
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; q4++) old_nxt[q4] = *reinterpret_cast<const uint4*>(orow + c0 + 32 + q4 * 8);
-                    }
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ch++) {
+                    const int c0 = cbeg + ch * 64;
+                    uint32_t r[64];
+                    tmem_ld32(tacc + c0, r);
+                    tmem_ld32(tacc + c0 + 32, r + 32);
                     tmem_ld_wait();
+                    if (lane == 0) bulk_wait_read<0>();      // the previous box has been read out of the staging buffer
+                    __syncwarp();
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        const uint32_t ov[4] = {old[q4].x, old[q4].y, old[q4].z, old[q4].w};
+                    for (int c = 0; c < 8; c++) {
                         uint32_t w[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            // bf16(acc) first, then the bf16 add (triton/csp_mlp_mm2.py:100-101)
-                            const uint32_t a = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]), __uint_as_float(r[q4 * 8 + 2 * j + 1]));
-                            w[j] = pack_bf16x2(bf16_lo(a) + bf16_lo(ov[j]), bf16_hi(a) + bf16_hi(ov[j]));
-                        }
-                        if (!(P.dbg & 16)) *reinterpret_cast<uint4*>(orow + c0 + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int j = 0; j < 4; j++)
+                            w[j] = pack_bf16x2(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]));
+                        st_shared_v4(stg + sw128_off(lane, c), w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(P.dbg & 16)) {
+                        tma_reduce_add_2d(&tmap_out, stg, nb * BN + c0, mb * BM + wq * 32);
+                        bulk_commit();
                     }
                 }
             }
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         setmaxnreg_dec<88>();     // warps 14-15: idle, setmaxnreg is warpgroup-wide
     }
 
+    if (IS_MM2 && warp < 8 && lane == 0) bulk_wait<0>();
     tc_fence_before_sync();
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc(tm, 512);
@@ -416,7 +423,7 @@ using namespace cm::mlp;
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <bool IS_MM2>
-static int launch_mlp(const CUtensorMap& tmap, Params& P, cudaStream_t stream) {
+static int launch_mlp(const CUtensorMap& tmap, const CUtensorMap& tmap_out, Params& P, cudaStream_t stream) {
     static bool configured = false;
     auto kern = mlp_kernel<IS_MM2>;
     if (!configured) {
@@ -426,7 +433,7 @@ static int launch_mlp(const CUtensorMap& tmap, Params& P, cudaStream_t stream) {
     }
     const int tiles = P.n_mb * P.n_nb;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, NUM_THREADS, IS_MM2 ? SMEM_MM2 : SMEM_MM1, stream>>>(tmap, P);
+    kern<<<grid, NUM_THREADS, IS_MM2 ? SMEM_MM2 : SMEM_MM1, stream>>>(tmap, tmap_out, P);
     return (int)cudaGetLastError();
 }
 
@@ -446,7 +453,7 @@ extern "C" int cm_csp_mlp_mm1(const void* a, const void* w1, void* c, const void
     P.M = M; P.K = K; P.F = F; P.N = F; P.idx_stride = idx_stride; P.update_pa = update_pa ? 1 : 0;
     P.n_mb = M / BM; P.n_nb = (F + BN - 1) / BN;
     P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
-    return launch_mlp<false>(tmap, P, (cudaStream_t)stream);
+    return launch_mlp<false>(tmap, tmap, P, (cudaStream_t)stream);
 }
 
 extern "C" int cm_csp_scatter_add(const void* packed, void* pa_T, const int32_t* indices, const int32_t* counts,
@@ -480,5 +487,8 @@ extern "C" int cm_csp_mlp_mm2(const void* packed, const void* w2_T, void* out, v
     P.M = M; P.K = F; P.F = F; P.N = N; P.idx_stride = idx_stride; P.update_pa = 0;
     P.n_mb = M / BM; P.n_nb = N / BN;
     P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
-    return launch_mlp<true>(tmap, P, (cudaStream_t)stream);
+    CUtensorMap tmap_out;      // out [M, N] in boxes of 32 rows x 64 columns (the epilogue's TMA reduce-add)
+    rc = encode_tmap_2d_bf16_sw128(&tmap_out, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32);
+    if (rc) return rc;
+    return launch_mlp<true>(tmap, tmap_out, P, (cudaStream_t)stream);
 }

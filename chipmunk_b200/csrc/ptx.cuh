@@ -161,6 +161,21 @@ __device__ __forceinline__ void bulk_reduce_add_bf16_s2g(void* dst, uint32_t src
                  "r"(src_smem), "r"(bytes)
                  : "memory");
 }
+// 2-D TMA store / reduce-add of one box from shared memory (layout = the tensor map's swizzle) to global.
+// The element type and the bf16 add (round-to-nearest, performed at the L2) come from the tensor map.
+__device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src_smem, int col, int row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(map), "r"(col),
+                 "r"(row), "r"(src_smem)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* map, uint32_t src_smem, int col, int row) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(map),
+                 "r"(col), "r"(row), "r"(src_smem)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {

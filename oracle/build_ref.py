@@ -1,0 +1,88 @@
+"""Build oracle/_ref/libchipmunk_ref_indexed_io.so from the reference's OWN sources, where they lie.
+
+    python oracle/build_ref.py [--force]
+
+Test infrastructure only.  The reference's attention / MLP kernels are ThunderKittens + wgmma
+(`-arch=sm_90a`, /root/reference/setup.py:76,101-105) and cannot be built for B200; its three index
+kernels are arch-generic CUDA + CUB + cuRAND and compile unmodified for sm_100a:
+
+    /root/reference/csrc/indexed_io/mask_to_indices.cu
+    /root/reference/csrc/indexed_io/topk_indices.cu
+    /root/reference/csrc/indexed_io/copy_indices.cu
+
+(`scatter_add.cu` includes kittens.cuh and is left out.)  They are compiled straight from
+/root/reference (never copied into this repo) together with `oracle/ref_shim.cpp`, which registers them
+as `torch.ops.chipmunk_ref.*`.  Output goes to `oracle/_ref/` only: git-ignored, NOT gpurun-ignored, so
+the built library travels to the GPU box where `tests/test_ref_kernels_gpu.py` runs the reference kernels
+next to ours.  /root/reference does not exist on the GPU box: nothing there rebuilds this.
+nvcc spends several minutes per file on <torch/extension.h>; the three files build in parallel.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("CHIPMUNK_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+LIB = os.path.join(OUT, "libchipmunk_ref_indexed_io.so")
+SOURCES = [os.path.join(REF, "csrc", "indexed_io", f)
+           for f in ("mask_to_indices.cu", "topk_indices.cu", "copy_indices.cu")]
+SHIM = os.path.join(HERE, "ref_shim.cpp")
+
+
+def available() -> bool:
+    return all(os.path.exists(s) for s in SOURCES)
+
+
+def build(force: bool = False) -> str | None:
+    if os.path.exists(LIB) and not force:
+        return LIB
+    if not available():
+        return None
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(OUT, exist_ok=True)
+    inc = [f"-I{p}" for p in ce.include_paths("cuda")]
+    import sysconfig
+    inc.append(f"-I{sysconfig.get_paths()['include']}")
+    common = ["-std=c++17", "-O3", "-Xcompiler", "-fPIC", "-DTORCH_API_INCLUDE_EXTENSION_H",
+              "-D_GLIBCXX_USE_CXX11_ABI=1", *inc]
+    cuflags = ["-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+               "--expt-extended-lambda", "-DNDEBUG", "--use_fast_math", "-DTORCH_COMPILE",   # setup.py:91-98
+               # torch.utils.cpp_extension's defaults (the reference is built through CUDAExtension, setup.py:124-133):
+               # without them at::Half comparisons in topk_indices.cu:20 are ambiguous with cuda_fp16.h's operators
+               "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
+               "-D__CUDA_NO_BFLOAT16_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__"]
+
+    def cc(src: str) -> str:
+        obj = os.path.join(OUT, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        flags = cuflags if src.endswith(".cu") else ["-x", "cu", *cuflags]
+        cmd = [nvcc, *common, *flags, "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(obj[:-2] + ".log", "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr[-4000:]}")
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(cc, [*SOURCES, SHIM]))
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
+           "-ltorch", "-lcurand"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    for o in objs:
+        os.remove(o)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build("--force" in sys.argv))
