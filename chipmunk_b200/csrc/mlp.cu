@@ -36,7 +36,8 @@ constexpr int A_BYTES = BM * 128;  // 16 KB
 constexpr int B_BYTES = BN * 128;  // 32 KB (mm1: 256 rows x 128 B; mm2: 4 n-chunks x 64 rows x 128 B)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int OUT_STAGE_BYTES = 32 * 128;            // mm2 epilogue: one 32-row x 64-column bf16 box per epilogue warp
-constexpr int SMEM_MM1 = 4 * STAGE_BYTES + 1024;
+constexpr int EPI1_BYTES = 2048;                     // mm1 epilogue, per warp: one 32x32 bf16 box of C, one 32-neuron x 32-token slice of the cache
+constexpr int SMEM_MM1 = 4 * STAGE_BYTES + 16 * EPI1_BYTES + 1024;
 constexpr int SMEM_MM2 = 4 * STAGE_BYTES + 8 * OUT_STAGE_BYTES + 1024;
 constexpr int NUM_THREADS = 512;   // warps 0-7 epilogue (two warpgroups, 128 columns each) | 8-11 gather | 12 MMA | 13 TMA | 14-15 idle
 constexpr int WARP_MMA = 12, WARP_TMA = 13, WARP_PROD0 = 8, NUM_EPI = 256;
@@ -76,8 +77,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_idx[IS_MM2 ? 1 : 2][IS_MM2 ? 1 : BN];          // mm1 epilogue: neuron index of each packed column of the tile
-    __shared__ float s_bias[IS_MM2 ? 1 : 2][IS_MM2 ? 1 : BN];       // mm1 epilogue: its bias
+    __shared__ __nv_bfloat16 s_bias[IS_MM2 ? 1 : 2][IS_MM2 ? 1 : BN];       // mm1 epilogue: bias of each packed column of the tile
 
     constexpr int STAGES = 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         fence_mbar_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
-    if (warp == WARP_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); if (IS_MM2) tma_prefetch_desc(&tmap_out); }
+    if (warp == WARP_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_out); }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -264,64 +264,90 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
             const int cbeg = half * (BN / 2);
             const int cend = min(ncols, cbeg + BN / 2);
             if constexpr (!IS_MM2) {
-                // stage this tile's neuron ids and biases (256 epilogue threads, one column each)
-                const int32_t* ip = P.indices + (int64_t)mb * P.idx_stride + nb * BN;
-                {
-                    const int c = tid;
-                    int f = c < ncols ? __ldg(ip + c) : 0;
-                    f = f < 0 ? 0 : (f >= P.F ? P.F - 1 : f);
-                    s_idx[buf][c] = f;
-                    s_bias[buf][c] = __bfloat162float(P.bias[f]);
-                }
+                // stage this tile's biases (256 epilogue threads, one packed column each)
+                const int32_t* ipt = P.indices + (int64_t)mb * P.idx_stride + nb * BN;
+                int f = tid < ncols ? __ldg(ipt + tid) : 0;
+                f = f < 0 ? 0 : (f >= P.F ? P.F - 1 : f);
+                s_bias[buf][tid] = P.bias[f];
                 named_bar_sync(1, NUM_EPI);
             }
             const uint32_t tacc = tm + buf * BN + lane_off;
             if (P.dbg & 8) {
                 mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
             } else if constexpr (!IS_MM2) {
+                // The weight gather saturates the LSU / L1 path, so the epilogue keeps off it: per 32-column chunk a
+                // warp (32 tokens) pulls its 32-neuron x 32-token slice of the cache into shared memory with 16-byte
+                // cp.async (one chunk ahead), and hands its 32 x 32 block of C to the TMA as one box store.
+                const int32_t* ip = P.indices + (int64_t)mb * P.idx_stride + nb * BN;
+                const uint32_t sY = sbase + STAGES * STAGE_BYTES + warp * EPI1_BYTES;      // C box, SWIZZLE_64B
+                const uint32_t sX = sY + 8 * EPI1_BYTES;                                   // cache slice [32 neurons][32 tokens]
+                const int m0 = mb * BM + wq * 32;
                 __nv_bfloat16* crow = P.out + (int64_t)m * P.F + nb * BN;
-                const unsigned short* pa_base = reinterpret_cast<const unsigned short*>(P.pa_T) + m;
-                // cached activations of the chunk's 32 neurons for this token: coalesced across the warp,
-                // fetched one chunk ahead (the first chunk before the accumulator is even ready)
-                unsigned short pa_cur[32], pa_nxt[32];
-                auto load_pa = [&](int c0, unsigned short (&dst)[32]) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        dst[j] = (c0 + j < cend) ? __ldg(pa_base + (int64_t)s_idx[buf][c0 + j] * P.M) : (unsigned short)0;
+                // lane j holds the neuron id of packed column c0 + j
+                auto load_f = [&](int c0) -> int {
+                    int f = (c0 + lane < cend) ? __ldg(ip + c0 + lane) : 0;
+                    return f < 0 ? 0 : (f >= P.F ? P.F - 1 : f);
                 };
-                if (cbeg < cend) load_pa(cbeg, pa_nxt);
+                auto fetch_pa = [&](int c0, int f_lane) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int row = 8 * i + (lane >> 2), piece = lane & 3;
+                        const int f = __shfl_sync(0xffffffffu, f_lane, row);
+                        if (c0 + row < cend) cp_async_16(sX + row * 64 + piece * 16, P.pa_T + (int64_t)f * P.M + m0 + piece * 8);
+                    }
+                    cp_async_commit();
+                };
+                int f_nxt = 0;
+                if (cbeg < cend) { f_nxt = load_f(cbeg); fetch_pa(cbeg, f_nxt); }
                 mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
                 tc_fence_after_sync();
                 for (int c0 = cbeg; c0 < cend; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(tacc + c0, r);
+                    const int f_cur = f_nxt;
+                    cp_async_wait_all();
+                    __syncwarp();
+                    uint32_t pa[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) pa_cur[j] = pa_nxt[j];
-                    if (c0 + 32 < cend) load_pa(c0 + 32, pa_nxt);
+                    for (int j = 0; j < 32; j++) pa[j] = ld_shared_u16(sX + j * 64 + lane * 2) << 16;
+                    __syncwarp();
+                    if (c0 + 32 < cend) { f_nxt = load_f(c0 + 32); fetch_pa(c0 + 32, f_nxt); }
                     tmem_ld_wait();
+                    const int nvalid = min(32, cend - c0);     // multiple of 16
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float p0 = __uint_as_float((uint32_t)pa_cur[j] << 16), p1 = __uint_as_float((uint32_t)pa_cur[j + 1] << 16);
-                        const float g0 = gelu_tanh(__uint_as_float(r[j]) + s_bias[buf][c0 + j]) - p0;
-                        const float g1 = gelu_tanh(__uint_as_float(r[j + 1]) + s_bias[buf][c0 + j + 1]) - p1;
+                        const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&s_bias[buf][c0 + j]));
+                        const float g0 = gelu_tanh(__uint_as_float(r[j]) + bb.x) - __uint_as_float(pa[j]);
+                        const float g1 = gelu_tanh(__uint_as_float(r[j + 1]) + bb.y) - __uint_as_float(pa[j + 1]);
                         pk[j >> 1] = pack_bf16x2(g0, g1);
                     }
                     if (P.update_pa) {
+                        unsigned short* pa_out = reinterpret_cast<unsigned short*>(P.pa_T) + m;
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            if (c0 + j < cend) {
+                            const int fj = __shfl_sync(0xffffffffu, f_cur, j);
+                            if (j < nvalid) {
                                 const float d = (j & 1) ? bf16_hi(pk[j >> 1]) : bf16_lo(pk[j >> 1]);
-                                const float old = __uint_as_float((uint32_t)pa_cur[j] << 16);
-                                P.pa_T[(int64_t)s_idx[buf][c0 + j] * P.M + m] = __float2bfloat16(old + d);
+                                pa_out[(int64_t)fj * P.M] = __bfloat16_as_ushort(__float2bfloat16(__uint_as_float(pa[j]) + d));
                             }
                         }
                     }
-                    const int nvalid = min(32, cend - c0);     // multiple of 16
+                    if (P.dbg & 16) continue;
+                    if (nvalid == 32) {
+                        if (lane == 0) bulk_wait_read<0>();          // the previous box has left the staging buffer
+                        __syncwarp();
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++)
-                        if (q4 * 8 < nvalid && !(P.dbg & 16))
-                            *reinterpret_cast<uint4*>(crow + c0 + q4 * 8) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+                        for (int c = 0; c < 4; c++)
+                            st_shared_v4(sY + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&tmap_out, sY, nb * BN + c0, m0); bulk_commit(); }
+                    } else {
+                        // ragged tail of the block's column list (count % 32 == 16): columns past `count` stay untouched
+                        *reinterpret_cast<uint4*>(crow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(crow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
                 }
             } else {
                 // O[m, tile columns] += bf16(acc): each warp packs its 32 rows x 64 columns into a 128B-swizzled
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         setmaxnreg_dec<88>();     // warps 14-15: idle, setmaxnreg is warpgroup-wide
     }
 
-    if (IS_MM2 && warp < 8 && lane == 0) bulk_wait<0>();
+    if (warp < 8 && lane == 0) bulk_wait<0>();
     tc_fence_before_sync();
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc(tm, 512);
@@ -453,7 +479,10 @@ extern "C" int cm_csp_mlp_mm1(const void* a, const void* w1, void* c, const void
     P.M = M; P.K = K; P.F = F; P.N = F; P.idx_stride = idx_stride; P.update_pa = update_pa ? 1 : 0;
     P.n_mb = M / BM; P.n_nb = (F + BN - 1) / BN;
     P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
-    return launch_mlp<false>(tmap, tmap, P, (cudaStream_t)stream);
+    CUtensorMap tmap_c;        // C [M, F] in boxes of 32 rows x 32 columns (the epilogue's TMA stores)
+    rc = encode_tmap_2d_bf16(&tmap_c, c, (uint64_t)M, (uint64_t)F, (uint64_t)F * 2, 32, 32, 64);
+    if (rc) return rc;
+    return launch_mlp<false>(tmap, tmap_c, P, (cudaStream_t)stream);
 }
 
 extern "C" int cm_csp_scatter_add(const void* packed, void* pa_T, const int32_t* indices, const int32_t* counts,

@@ -16,6 +16,11 @@ namespace cm {
 int encode_tmap_2d_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                               uint64_t pitch_bytes, uint32_t box_rows);
 
+// General form: boxes of `box_rows` x `box_cols` elements; `swizzle_bytes` in {0, 32, 64, 128} must be >= the
+// box's inner extent in bytes (or 0).  Used for the epilogue stores (shared -> global boxes).
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                        uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+
 // One thread: load the tile whose top-left element is (row, col) into `dst` (1024-byte aligned),
 // completing `bytes` on `bar`.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
