@@ -7,7 +7,8 @@ Workload ("flux_single_stream_block"): one SPARSE denoising step of one FLUX.1-d
 block on synthetic tensors: column-sparse delta attention over N = 4096 image + 512 text tokens,
 H = 24 heads, d = 128, 83.5 % column sparsity (count = 112*round(0.165*N/112) keys per 192-query
 group, the fused `csp_attn` path), then the column-sparse MLP (d = 3072, F = 12288, 70 % sparse:
-3840 active neurons per 128-token block).  A step = csp_attn + csp_mlp_mm1 + csp_mlp_mm2.
+3840 active neurons per 128-token block).  A step = csp_attn_add (cache + sparse delta,
+one kernel) + csp_mlp_mm1 + csp_mlp_mm2, the three launches of the modules' sparse step.
 
 metric = dense-equivalent TFLOP/s: FLOPs the DENSE block would need (4*N^2*d*H + 4*M*K*F)
 divided by the sparse step time.  `value` has inputs resident in HBM; `e2e` feeds the same step
@@ -179,8 +180,7 @@ def run_ours(args):
 
     def step(ev=None):
         if ev is not None: ev[0].record()
-        blk.o.copy_(blk.o_cache)                                   # the module clones the cache before the in-place add
-        torch.ops.chipmunk.csp_attn(blk.q, blk.k, blk.v, blk.o, blk.a_idx, blk.a_cnt, 1)
+        T.csp_attn_add(blk.q, blk.k, blk.v, blk.o_cache, blk.a_idx, blk.a_cnt, 1, out=blk.o)   # SparseDiffAttn's sparse step
         if ev is not None: ev[1].record()
         T.mlp_mm1(blk.x, blk.w1, blk.packed, blk.b1, blk.pa_T, blk.m_idx, blk.m_cnt, True)
         if ev is not None: ev[2].record()
@@ -234,7 +234,7 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src}
 
     kernels = {
-        "csp_attn(+cache clone)": (t_attn, roof(attn_alg_bytes(H, NSEQ, ATTN_COUNT), t_attn, traffic_db.get("csp_attn(+cache clone)"))),
+        "csp_attn_add": (t_attn, roof(attn_alg_bytes(H, NSEQ, ATTN_COUNT), t_attn, traffic_db.get("csp_attn_add"))),
         "csp_mlp_mm1": (t_mm1, roof(mm1_alg_bytes(M, MLP_COUNT), t_mm1, traffic_db.get("csp_mlp_mm1"))),
         "csp_mlp_mm2": (t_mm2, roof(mm2_alg_bytes(M, MLP_COUNT), t_mm2, traffic_db.get("csp_mlp_mm2"))),
     }
@@ -242,7 +242,7 @@ def run_ours(args):
     roofline = dict(kernels[dominant][1])
     roofline["kernel"] = dominant
     roofline["launch_us"] = round(kernels[dominant][0] * 1e3, 1)
-    sparse_flops = {"csp_attn(+cache clone)": 4.0 * QG * ATTN_COUNT * D * H * ((NSEQ + QG - 1) // QG),
+    sparse_flops = {"csp_attn_add": 4.0 * QG * ATTN_COUNT * D * H * ((NSEQ + QG - 1) // QG),
                     "csp_mlp_mm1": 2.0 * M * MLP_COUNT * MLP_K, "csp_mlp_mm2": 2.0 * M * MLP_COUNT * MLP_K}
     per_kernel = {k: {"us": round(v[0] * 1e3, 1), "gather_roofline_frac": v[1]["frac"],
                       "tensor_tflops": round(sparse_flops[k] / (v[0] * 1e-3) / 1e12, 1),
@@ -279,8 +279,7 @@ def run_ours(args):
             if i >= 2:
                 stream.wait_event(ev_out[j])                 # step i-2's results have left obuf[j] / ostage[j]
             q_, k_, v_, x_ = inbuf[j]
-            obuf[j].copy_(blk.o_cache)
-            torch.ops.chipmunk.csp_attn(q_, k_, v_, obuf[j], blk.a_idx, blk.a_cnt, 1)
+            T.csp_attn_add(q_, k_, v_, blk.o_cache, blk.a_idx, blk.a_cnt, 1, out=obuf[j])
             cm.ops.mlp(x_, blk.w1, blk.b1, blk.w2t, blk.m_idx, blk.m_cnt, blk.pa_T, blk.out_cache, 6)
             ostage[j].copy_(blk.out_cache)
             ev_comp[j].record(stream)
@@ -388,7 +387,7 @@ def c3_attention(dev, world, rank):
     from chipmunk_b200 import parallel
 
     def layer():
-        # cache clone + csp_attn on this rank's heads + ONE all-gather of O
+        # csp_attn_add on this rank's heads, written into the gather buffer + ONE (in-place) all-gather of O
         return parallel.sparse_attention_head_parallel(q, k, v, o, idx, cnt, hl * world)
 
     for _ in range(2):

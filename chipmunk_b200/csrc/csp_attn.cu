@@ -54,11 +54,13 @@ struct Params {
     const int32_t* indices;      // null in dense mode
     const int32_t* counts;       // null in dense mode
     float* l;                    // dense mode: [B,H,Nq]
+    const __nv_bfloat16* cache;  // fused add-back: o = bf16(cache + o_scale * delta), out of place (null: see `accumulate`)
     int B, H, Nq, Nk, G;
-    int64_t qs[3], ks[3], vs[3], os[3];
+    int64_t qs[3], ks[3], vs[3], os[3], cs[3];
     int64_t idx_row_stride;
     float o_scale;
     int accumulate;
+    int wide;                    // o (and cache) rows are 32-byte aligned: the epilogue moves full sectors per access
     int num_tiles;
     int dbg;                     // CM_DEBUG_FLAGS: timing experiments only (results are wrong when set)
 };
@@ -287,7 +289,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             const bool row_ok = row < P.Nq;
             __nv_bfloat16* orow = P.o + b * P.os[0] + h * P.os[1] + (int64_t)(row_ok ? row : 0) * P.os[2];
             if (count <= 0) {
-                if (!P.accumulate && row_ok) {
+                if (!DENSE && P.cache != nullptr) {
+                    if (row_ok) {
+                        const uint4* crow = reinterpret_cast<const uint4*>(P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)row * P.cs[2]);
+#pragma unroll
+                        for (int c = 0; c < 16; c++) reinterpret_cast<uint4*>(orow)[c] = __ldg(crow + c);
+                    }
+                } else if (!P.accumulate && row_ok) {
 #pragma unroll
                     for (int c = 0; c < 16; c++) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0, 0, 0, 0);
                 }
@@ -309,26 +317,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                 mbar_arrive(&bar.p_full[blk]);
             }
             // ---- epilogue: O / l * scale (+ cached o) -> bf16
+            // fused add-back: this row of the cached output is requested before the last P.V lands
+            const bool fused = !DENSE && P.cache != nullptr;
+            const __nv_bfloat16* crow = P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)(row_ok ? row : 0) * P.cs[2];
+            uint32_t cv[4][8];                         // half a row of the cache: 4 sectors of 32 bytes
+            auto load_cache_half = [&](int hf) {
+                if (P.wide) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) ld_global_nc_v8(crow + hf * 64 + c * 16, cv[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const uint4 t = ld_global_nc_v4(crow + hf * 64 + c * 8);
+                        cv[c >> 1][(c & 1) * 4 + 0] = t.x; cv[c >> 1][(c & 1) * 4 + 1] = t.y;
+                        cv[c >> 1][(c & 1) * 4 + 2] = t.z; cv[c >> 1][(c & 1) * 4 + 3] = t.w;
+                    }
+                }
+            };
+            if (fused) load_cache_half(0);
             mbar_wait(&bar.o_full[blk], oc & 1); oc++;
             tc_fence_after_sync();
             const float inv = P.o_scale / l_sum;
             if (DENSE && row_ok && P.l) P.l[(int64_t)bh * P.Nq + row] = 1.f / (fast_exp2(m_ref * SCALE_LOG2) * l_sum);
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tO + c0, r);
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t r[64];
+                tmem_ld32(tO + hf * 64, r);
+                tmem_ld32(tO + hf * 64 + 32, r + 32);
                 tmem_ld_wait();
+                uint32_t w[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) w[j] = pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+                if (fused) {
+                    // o = bf16(cache + bf16(delta)), written out of place: no clone of the cache, no read-modify-write
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            w[8 * c + j] = pack_bf16x2(bf16_lo(cv[c][j]) + bf16_lo(w[8 * c + j]), bf16_hi(cv[c][j]) + bf16_hi(w[8 * c + j]));
+                    if (hf == 0) load_cache_half(1);
+                }
                 if (row_ok) {
+                    if (!fused && P.accumulate) {
+                        // in-place delta add-back (csp_attn): o = bf16(o + delta) as 16-byte reductions at the L2 (the
+                        // reference uses a TMA reduce-add, csp_attn.cu:300)
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        uint32_t w[4];
+                        for (int c = 0; c < 8; c++)
+                            red_add_bf16x8(orow + hf * 64 + c * 8, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                    } else if (P.wide) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            w[j] = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2 * j]) * inv, __uint_as_float(r[q4 * 8 + 2 * j + 1]) * inv);
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c0 + q4 * 8);
-                        // the delta add-back: o = bf16(o + delta) as a 16-byte reduction at the L2 (the reference
-                        // uses a TMA reduce-add, csp_attn.cu:300); plain store for csp_128_attn / dense
-                        if (P.accumulate) red_add_bf16x8(dst, w[0], w[1], w[2], w[3]);
-                        else *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int c = 0; c < 4; c++) st_global_v8(orow + hf * 64 + c * 16, w + 8 * c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            *reinterpret_cast<uint4*>(orow + hf * 64 + c * 8) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
                     }
                 }
             }
@@ -382,10 +424,10 @@ int launch(const void* q, const void* k, const void* v, void* o, float* l, const
            int64_t idx_row_stride, int o_scale, int accumulate, int dense, cudaStream_t stream);
 } }
 
-extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,
-                           const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
-                           const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
-                           int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
+static int csp_attn_impl(const void* q, const void* k, const void* v, const void* cache, void* o, const int32_t* indices,
+                         const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
+                         const int64_t k_strides[3], const int64_t v_strides[3], const int64_t c_strides[3],
+                         const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
     if (B < 0 || H < 0 || Nq < 0 || Nk <= 0 || idx_row_stride <= 0) return CM_EINVAL;
     if (o_scale != 1 && o_scale != -1) return CM_EINVAL;
     if ((int64_t)B * H * Nq == 0) return CM_OK;
@@ -393,30 +435,57 @@ extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return CM_EALIGN;
     if (!strides_ok(q_strides) || !strides_ok(k_strides) || !strides_ok(v_strides) || !strides_ok(o_strides))
         return CM_EALIGN;
+    if (cache && (!aligned16(cache) || !strides_ok(c_strides) || cache == o)) return cache == o ? CM_EINVAL : CM_EALIGN;
     if (!is_sm100()) return CM_EARCH;
     // CM_ATTN_V2=1 selects the experimental CTA-pair kernel (csp_attn2.cu: correct, not yet faster)
     static const bool use_v2 = getenv("CM_ATTN_V2") && atoi(getenv("CM_ATTN_V2")) != 0;
     static const bool use_v3 = getenv("CM_ATTN_V3") && atoi(getenv("CM_ATTN_V3")) != 0;
-    if (use_v3)
+    if (use_v3 && !cache)
         return cm::attn3::launch(q, k, v, o, nullptr, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
                                  idx_row_stride, o_scale, accumulate, 0, (cudaStream_t)stream);
-    if (use_v2)
+    if (use_v2 && !cache)
         return cm::attn2::launch(q, k, v, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
                                  idx_row_stride, o_scale, accumulate, (cudaStream_t)stream);
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
     P.o = (__nv_bfloat16*)o;
     P.indices = indices; P.counts = counts; P.l = nullptr;
+    P.cache = (const __nv_bfloat16*)cache;
     P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
-    for (int i = 0; i < 3; i++) { P.qs[i] = q_strides[i]; P.ks[i] = k_strides[i]; P.vs[i] = v_strides[i]; P.os[i] = o_strides[i]; }
+    for (int i = 0; i < 3; i++) {
+        P.qs[i] = q_strides[i]; P.ks[i] = k_strides[i]; P.vs[i] = v_strides[i]; P.os[i] = o_strides[i];
+        P.cs[i] = cache ? c_strides[i] : 0;
+    }
     P.idx_row_stride = idx_row_stride;
     P.o_scale = (float)o_scale;
     P.accumulate = accumulate ? 1 : 0;
+    auto wide_ok = [](const void* p, const int64_t st[3]) {
+        return (reinterpret_cast<uintptr_t>(p) & 31) == 0 && st[0] % 16 == 0 && st[1] % 16 == 0 && st[2] % 16 == 0;
+    };
+    P.wide = wide_ok(o, o_strides) && (!cache || wide_ok(cache, c_strides)) ? 1 : 0;
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
     P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
     return launch_attn<false>(P, (cudaStream_t)stream);
+}
+
+extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,
+                           const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
+                           const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
+                           int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
+    return csp_attn_impl(q, k, v, nullptr, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, nullptr,
+                         o_strides, idx_row_stride, o_scale, accumulate, stream);
+}
+
+extern "C" int cm_csp_attn_add(const void* q, const void* k, const void* v, const void* cache, void* o,
+                               const int32_t* indices, const int32_t* counts, int B, int H, int Nq, int Nk,
+                               const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                               const int64_t cache_strides[3], const int64_t o_strides[3], int64_t idx_row_stride,
+                               int o_scale, void* stream) {
+    if (!cache || !cache_strides) return CM_EINVAL;
+    return csp_attn_impl(q, k, v, cache, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, cache_strides,
+                         o_strides, idx_row_stride, o_scale, 0, stream);
 }
 
 namespace cm { namespace attn {
@@ -443,6 +512,8 @@ extern "C" int cm_dense_attn(const void* q, const void* k, const void* v, void* 
     P.idx_row_stride = Nk;
     P.o_scale = 1.f;
     P.accumulate = 0;
+    P.wide = (reinterpret_cast<uintptr_t>(o) & 31) == 0 ? 1 : 0;
+    P.cache = nullptr;
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;

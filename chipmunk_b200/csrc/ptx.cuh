@@ -176,6 +176,24 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* map, uint32_t src_
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 16-byte read-only global load that stays where it is written (asm volatile: the compiler may not hoist it
+// into a region with higher register pressure the way it does with __ldg).
+__device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// 32-byte (one full sector) global load / store: a thread that owns a whole row moves it in full sectors, which
+// halves the L1 sector operations of the row-strided epilogues compared with 16-byte accesses.
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(addr) : "memory");

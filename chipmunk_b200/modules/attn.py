@@ -130,19 +130,18 @@ class SparseDiffAttn(nn.Module):
                 o = ops.dense_attn(q, k, v)[0]
             if not cfg["recompute_mask"] or inds is None:
                 inds, counts = self._stored_indices(multiple_of, bm)
-            # cache = dense - sparse, with the subtraction done by the kernel epilogue
-            o_cache = o.clone()
-            torch.ops.chipmunk.csp_attn(q, k, v, o_cache, inds, counts, -1)
-            self.storage.set_out_cache(o_cache)
+            # cache = dense - sparse, written by the kernel epilogue in one pass (no clone, no read-modify-write)
+            self.storage.set_out_cache(ops.csp_attn_add(q, k, v, o, inds, counts, -1))
             return o
 
         # sparse step: out = cache + sparse(q, k, v), accumulated in the kernel epilogue
         inds, counts = self._stored_indices(multiple_of, bm)
-        o = self.storage.get_out_cache()
-        if not self.storage.out_cache.is_offload_enabled:
-            o = o.clone()          # the cache must survive; offloaded caches are reloaded anyway
-        torch.ops.chipmunk.csp_attn(q, k, v, o, inds, counts, 1)
-        return o
+        cache = self.storage.get_out_cache()
+        if self.storage.out_cache.is_offload_enabled:
+            # an offloaded cache was just reloaded into a scratch buffer: accumulate in place, like the reference
+            torch.ops.chipmunk.csp_attn(q, k, v, cache, inds, counts, 1)
+            return cache
+        return ops.csp_attn_add(q, k, v, cache, inds, counts, 1)   # the resident cache must survive
 
     def forward(self, q: Tensor, k: Tensor, v: Tensor) -> Tensor:
         if not GLOBAL_CONFIG["attn"]["is_enabled"]:

@@ -22,6 +22,13 @@ def csp_attn(q, k, v, indices, indices_counts):
     return torch.ops.chipmunk.csp_128_attn(q, k, v, indices, indices_counts)
 
 
+def csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale: int = 1, out=None):
+    """cache + o_scale * csp(q, k, v) in one kernel, out of place (B200 addition; replaces the
+    `clone` + in-place `torch.ops.chipmunk.csp_attn` pair of reference modules/attn.py:165-190)."""
+    from .. import torch_ops as _t
+    return _t.csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale, out)
+
+
 def dense_attn(q, k, v):
     """Returns (o [B,H,N,128], l [B,H,pad192(N),1]) with l zero past N, the shape the reference
     hands back so that it can be fed to dense_colsum_attn (ops/attn.py:42-84)."""
@@ -49,4 +56,4 @@ def dense_colsum_attn(q, k, v, p):
     return o, cs, l
 
 
-__all__ = ["csp_attn", "dense_attn", "dense_colsum_attn"]
+__all__ = ["csp_attn", "csp_attn_add", "dense_attn", "dense_colsum_attn"]

@@ -53,6 +53,17 @@ def all_gather_heads(o_local: torch.Tensor, num_heads: int, group=None) -> torch
 def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
     """One sparse attention step with heads sharded over the ranks of `group`.
     q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output."""
-    o = o_cache.clone()
-    torch.ops.chipmunk.csp_attn(q, k, v, o, indices, counts, 1)
+    from . import torch_ops as _t
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    B, h_local, N, D = q.shape
+    if world > 1 and num_heads % world == 0:
+        # the kernel writes cache + delta straight into this rank's slice of the gather buffer (rank-major), and
+        # the all-gather runs in place on it: no clone of the cache, no staging copy of O
+        rank = dist.get_rank(group)
+        out = q.new_empty(world, B, h_local, N, D)
+        _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1, out=out[rank])
+        dist.all_gather_into_tensor(out.view(world * B, h_local, N, D), out[rank], group=group)
+        return out.permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
+    o = _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1)
     return all_gather_heads(o, num_heads, group)

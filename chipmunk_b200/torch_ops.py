@@ -87,6 +87,32 @@ def csp_attn(q, k, v, o, indices, indices_counts, o_scale):
     _launch_csp_attn(q, k, v, o, indices, indices_counts, o_scale, 1)
 
 
+def csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale: int = 1, out=None):
+    """o = bf16(cache + o_scale * delta) as a fresh tensor, or into `out` (any [B,H,N,128] bf16 view with
+    16-byte-aligned strides, e.g. this rank's slice of an all-gather buffer).  B200 addition: the sparse
+    step's `o = cache.clone(); csp_attn(..., o, ...)` in one pass; `cache` is left untouched."""
+    _chk(o_scale in (1, -1), "o_scale must be 1 or -1")
+    B, H, Nq, Nk = _attn_common_checks(q, k, v, indices, indices_counts, "csp_attn_add")
+    _chk(cache.shape == q.shape and cache.dtype == torch.bfloat16 and cache.stride(3) == 1, "cache must match Q")
+    _chk(all(s % 8 == 0 for s in cache.stride()[:3]) and cache.data_ptr() % 16 == 0, "cache must be 16-byte aligned")
+    require_cuda(cache)
+    if out is None:
+        o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    else:
+        o = out
+        require_cuda(o)
+        _chk(o.shape == q.shape and o.dtype == torch.bfloat16 and o.stride(3) == 1, "out must match Q")
+        _chk(all(s % 8 == 0 for s in o.stride()[:3]) and o.data_ptr() % 16 == 0, "out must be 16-byte aligned")
+        _chk(o.data_ptr() != cache.data_ptr(), "out must not alias cache (use csp_attn for the in-place form)")
+    if B * H * Nq == 0:
+        return o
+    with torch.cuda.device(q.device):
+        check(lib.cm_csp_attn_add(_ptr(q), _ptr(k), _ptr(v), _ptr(cache), _ptr(o), _ptr(indices), _ptr(indices_counts),
+                                  B, H, Nq, Nk, strides3(q), strides3(k), strides3(v), strides3(cache), strides3(o),
+                                  indices.shape[3], int(o_scale), stream_ptr(q.device)), "csp_attn_add")
+    return o
+
+
 def csp_128_attn(q, k, v, indices, indices_counts):
     o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
     _launch_csp_attn(q, k, v, o, indices, indices_counts, 1, 0)

@@ -58,6 +58,20 @@ int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
                 const int64_t v_strides[3], const int64_t o_strides[3],
                 int64_t idx_row_stride, int o_scale, int accumulate, void* stream);
 
+/* The same kernel with the delta add-back written OUT OF PLACE:
+ *     o[b,h,rows of g] = bf16(cache + delta),   cache != o, cache is not modified.
+ * Replaces the `o = o_cache.clone(); csp_attn(q, k, v, o, ...)` pair of the reference's sparse step
+ * (src/chipmunk/modules/attn.py:186-190) and the `o_cache = o - csp(...)` of its full step (:165-170, o_scale = -1):
+ * one pass over the cache instead of clone + read-modify-write.  Numerically identical to cm_csp_attn(accumulate=1)
+ * on a copy of the cache (delta is rounded to bf16 first, then one bf16 add).
+ */
+int cm_csp_attn_add(const void* q, const void* k, const void* v, const void* cache, void* o,
+                    const int32_t* indices, const int32_t* counts,
+                    int B, int H, int Nq, int Nk,
+                    const int64_t q_strides[3], const int64_t k_strides[3],
+                    const int64_t v_strides[3], const int64_t cache_strides[3], const int64_t o_strides[3],
+                    int64_t idx_row_stride, int o_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Dense attention with the statistics the sparse steps need.
  * Replaces chipmunk::dense_attn        (csrc/attn/dense_attn.cu:246-371, schema chipmunk.cpp:54)

@@ -66,6 +66,34 @@ def test_csp_attn_matches_oracle(cm, oracle, cuda, B, H, N, count, strided):
         _close(o, ref)
 
 
+@pytest.mark.parametrize("B,H,N,count,strided", [(1, 2, 384, 128, False), (2, 3, 500, 112, True), (1, 1, 777, 200, False)])
+def test_csp_attn_add_equals_clone_plus_accumulate(cm, oracle, cuda, B, H, N, count, strided):
+    """The fused out-of-place add-back (cm_csp_attn_add) must be BIT-identical to the reference sequence
+    `o = cache.clone(); csp_attn(q, k, v, o, idx, cnt, s)` (modules/attn.py:165-190), for s = +1 and -1, must leave
+    the cache untouched, must copy the cache through for groups with count 0, and must match the oracle."""
+    gen = torch.Generator().manual_seed(99 + N)
+    q, k, v = _rand_qkv(B, H, N, N, gen, strided)
+    G = (N + 191) // 192
+    idx, cnt = oracle.random_index_sets(B, H, G, N, count, gen)
+    idx_full = torch.zeros(B, H, G, N, dtype=torch.int32)
+    idx_full[..., :count] = idx
+    cnt[0, 0, G - 1] = 0                                   # one empty group
+    cache = torch.randn(B, H, N, 128, generator=gen).to(torch.bfloat16)
+    dq, dk, dv = q.to(cuda), k.to(cuda), v.to(cuda)
+    if strided:
+        dq, dk, dv = (t.permute(2, 0, 1, 3).contiguous().permute(1, 2, 0, 3) for t in (dq, dk, dv))
+    di, dc, dcache = idx_full.to(cuda), cnt.to(cuda), cache.to(cuda)
+    for sc in (1, -1):
+        two_pass = dcache.clone()
+        torch.ops.chipmunk.csp_attn(dq, dk, dv, two_pass, di, dc, sc)
+        fused = cm.ops.csp_attn_add(dq, dk, dv, dcache, di, dc, sc)
+        assert torch.equal(dcache.cpu(), cache), "the cache must not be modified"
+        assert torch.equal(fused, two_pass), "fused add-back differs from clone + in-place accumulate"
+        _close(fused, oracle.csp_attn(q, k, v, cache, idx_full, cnt, sc))
+    rows = slice((G - 1) * 192, N)
+    assert torch.equal(fused[0, 0, rows].cpu(), cache[0, 0, rows])
+
+
 def test_csp_attn_identity_indices_is_sdpa(cm, oracle, cuda):
     """The reference's own known-answer test (src/chipmunk/tests/test_csp_attn.py:30-38):
     indices = arange(n), counts = n, o = 0, o_scale = 1  ==>  F.scaled_dot_product_attention."""
