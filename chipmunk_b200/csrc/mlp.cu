@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
         setmaxnreg_dec<88>();
         const int pt = tid - WARP_PROD0 * 32;
         uint32_t it = 0;       // global stage counter
+        // the weight matrix (75 MB at FLUX sizes) is the only operand with reuse across token blocks: keep it in
+        // L2 against the streaming token / cache / output traffic
+        const uint64_t pol_w = l2_policy_evict_last();
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mb, nb, ncols, ksteps, klast;
             tile_shape(tile, mb, nb, ncols, ksteps, klast);
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                     for (int i = 0; i < 16; i++) {
                         const int r = r0 + 16 * i;
                         if (((okm >> i) & 1u) && !(P.dbg & 1))
-                            cp_async_16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src[i] + ks * BK);
+                            cp_async_16_hint(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src[i] + ks * BK, pol_w);
                     }
                     cp_async_mbar_arrive_noinc(&bar.full[s]);
                 }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                             const int r = w + 4 * i;
                             int f = __shfl_sync(0xffffffffu, f_cur, i);
                             f = f >= P.F ? P.F - 1 : f;
-                            if (f >= 0 && !(P.dbg & 1)) cp_async_16(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N);
+                            if (f >= 0 && !(P.dbg & 1)) cp_async_16_hint(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N, pol_w);
                         }
                         cp_async_mbar_arrive_noinc(&bar.full[s]);
                         it++;

@@ -118,6 +118,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ void cp_async_16_hint(uint32_t dst_smem, const void* src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_16_zfill_hint(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint64_t policy) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst_smem), "l"(src),
                  "r"(src_bytes), "l"(policy)

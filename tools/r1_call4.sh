@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_attn_gpu.py tests/test_modules_gpu.py -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/c4_pytest.txt
+for f in 0 32; do echo "flags=$f";
+CM_DEBUG_FLAGS=$f timeout 200 python tools/quick_attn.py 4608 784 1 24 20 2>&1 | head -1
+CM_DEBUG_FLAGS=$f timeout 200 python tools/quick_attn.py 16384 2944 1 24 10 2>&1 | head -1
+CM_DEBUG_FLAGS=$f timeout 200 python tools/quick_attn.py 119056 8320 1 24 4 2>&1 | head -1
+done 2>&1 | tee gpurun_out/c4_attn.txt
