@@ -105,7 +105,7 @@ colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 mbar_wait(&bar.k_full[s], (kc / KSTAGES) & 1);
                 mbar_wait(&bar.acc_empty[ab], ((kc >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int k16 = 0; k16 < D / 16; k16++) {
                         const uint64_t ad = umma_smem_desc(sK + s * K_BYTES + (k16 >> 2) * (K_BYTES / 2) + (k16 & 3) * 32, 16, 1024);

@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
         const uint64_t desc_k = umma_smem_desc(sKV, 16, 1024);                   // K-major B: gathered K rows
         const uint64_t desc_v = umma_smem_desc(sKV, SLOT_BYTES / 2, 1024);       // MN-major B: gathered V rows
+        // Every MMA batch is issued under elect.sync: ptxas then emits the UTCHMMAs back to back.  With a lane test
+        // (`lane == 0`) it wraps each one in an ELECT / branch loop (~25 cycles per MMA, ~800 per step) during which
+        // the tensor pipe drains.
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
             const int count = tile_count(P, tile, DENSE);
             if (count <= 0) { it--; continue; }
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             uint32_t slotK = job % NSLOT;
             mbar_wait(&bar.kv_full[slotK], (job / NSLOT) & 1);
             tc_fence_after_sync();
-            if (lane == 0) {
+            if (elect_one()) {
                 issue_S(0, slotK, ncols(0)); umma_commit(&bar.s_full[0]);
                 issue_S(1, slotK, ncols(0)); umma_commit(&bar.s_full[1]);
                 umma_commit(&bar.kv_empty[slotK]);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                 // block 0
                 mbar_wait(&bar.p_full[0], sc0 & 1); sc0++;
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {
                     issue_PV(0, slotV, ncols(kk), kk == 0);
                     if (more) { issue_S(0, slotKn, ncols(kk + 1)); umma_commit(&bar.s_full[0]); }
                     else umma_commit(&bar.o_full[0]);
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
                 // block 1
                 mbar_wait(&bar.p_full[1], sc1 & 1); sc1++;
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {
                     issue_PV(1, slotV, ncols(kk), kk == 0);
                     umma_commit(&bar.kv_empty[slotV]);
                     if (more) {

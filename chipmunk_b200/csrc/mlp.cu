@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 const uint32_t s = it % STAGES;
                 mbar_wait(&bar.full[s], (it / STAGES) & 1);
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {      // elect.sync: ptxas emits the UTCHMMAs back to back (a lane test costs a per-instruction ELECT loop)
                     const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
                     const int k16s = (ks == ksteps - 1 ? klast : BK) / 16;
                     for (int k16 = 0; k16 < ((P.dbg & 4) ? 0 : k16s); k16++) {
