@@ -6,9 +6,11 @@
 // N = 192 queries on the columns), so the sum over the group's queries is a per-thread loop
 // over TMEM columns: no atomics, no shuffles, fp32 accumulation, one bf16 rounding.
 //
-//   warp 5     TMA: Q group tile once per (b,h,g) (double-buffered), K tiles through a 3-stage ring
-//   warp 4     MMA issuer: tcgen05.mma M=128 N=192 K=128 into one of two TMEM accumulators
-//   warps 0-3  one thread per key: sum_i exp2(s*c + log2 p_i) over the 192 columns, bf16 store
+//   warp 5      TMA: Q group tile once per (b,h,g) (double-buffered), K tiles through a 3-stage ring
+//   warp 4      MMA issuer: tcgen05.mma M=128 N=192 K=128 into one of two TMEM accumulators
+//   warps 0-3   one thread per key, query columns 0-95:  sum_i exp2(s*c + log2 p_i), adds the partner's partial, bf16 store
+//   warps 8-11  the same keys, query columns 96-191 (two exp warps per SM sub-partition: a single warp can issue
+//               a MUFU.EX2 only every ~8.8 cycles and nothing else meanwhile; two interleave and fill the MUFU pipe)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,7 +30,7 @@ constexpr int Q_BYTES = 2 * QG * 128;       // 49152: two 64-wide d-halves
 constexpr int K_BYTES = 2 * KT * 128;       // 32768
 constexpr int KSTAGES = 3;
 constexpr int SMEM_BYTES = 2 * Q_BYTES + KSTAGES * K_BYTES + 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 384;    // warps 0-3 exp A | 4 MMA | 5 TMA | 6-7 idle | 8-11 exp B
 constexpr float SCALE_LOG2 = 0.08838834764f * 1.44269504089f;
 
 struct Params {
@@ -51,6 +53,7 @@ colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     __shared__ Barriers bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_lp[2][QG];     // log2(p_i) of the tile's query rows
+    __shared__ float s_part[2][KT];                 // partial sums of the second exp group
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -59,7 +62,7 @@ colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&bar.q_full[i], 1); mbar_init(&bar.q_empty[i], 1);
-            mbar_init(&bar.acc_full[i], 1); mbar_init(&bar.acc_empty[i], 128);
+            mbar_init(&bar.acc_full[i], 1); mbar_init(&bar.acc_empty[i], 256);
         }
         for (int i = 0; i < KSTAGES; i++) { mbar_init(&bar.k_full[i], 1); mbar_init(&bar.k_empty[i], 1); }
         fence_mbar_init();
@@ -119,45 +122,64 @@ colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < 4 || warp >= 8) {
         // ======================================================================= exp + column sum
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        const int key_in_tile = warp * 32 + lane;
+        const int grp = warp >> 3;                        // 0: query columns 0-95, 1: columns 96-191
+        const int wq = warp & 3;                          // TMEM lane quadrant = SM sub-partition
+        const int et = grp * 128 + wq * 32 + lane;        // 0..255 over the two exp groups
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const int key_in_tile = wq * 32 + lane;
+        const int cbeg = grp * (QG / 2);
         uint32_t tcount = 0, kc = 0;
+        const uint64_t c2 = pack_f32x2(SCALE_LOG2, SCALE_LOG2);
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, tcount++) {
             const int g = tile % P.G, bh = tile / P.G;
             const uint32_t lb = tcount & 1;
-            for (int i = tid; i < QG; i += 128) {
-                const int row = g * QG + i;
+            if (et < QG) {
+                const int row = g * QG + et;
                 const float pv = row < P.Nq ? __ldg(P.p + (int64_t)bh * P.Nq + row) : 0.f;
-                s_lp[lb][i] = pv > 0.f ? __log2f(pv) : -INFINITY;
+                s_lp[lb][et] = pv > 0.f ? __log2f(pv) : -INFINITY;
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             __nv_bfloat16* crow = P.cs + (int64_t)tile * P.cs_stride;
             for (int kt = 0; kt < P.n_kt; kt++, kc++) {
                 const uint32_t ab = kc & 1;
                 mbar_wait(&bar.acc_full[ab], (kc >> 1) & 1);
                 tc_fence_after_sync();
-                const uint32_t tacc = tm + ab * 256 + lane_off;
-                float acc0 = 0.f, acc1 = 0.f;
+                const uint32_t tacc = tm + ab * 256 + lane_off + cbeg;
+                uint64_t acc[2] = {0ull, 0ull};
 #pragma unroll 1
-                for (int c0 = 0; c0 < QG; c0 += 32) {
+                for (int c0 = 0; c0 < QG / 2; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(tacc + c0, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 lp = *reinterpret_cast<const float4*>(&s_lp[lb][c0 + j]);
-                        acc0 += fast_exp2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, lp.x));
-                        acc1 += fast_exp2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, lp.y));
-                        acc0 += fast_exp2(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, lp.z));
-                        acc1 += fast_exp2(fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, lp.w));
+                        const float4 lp = *reinterpret_cast<const float4*>(&s_lp[lb][cbeg + c0 + j]);
+                        const uint64_t xa = ffma2(pack_f32x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack_f32x2(lp.x, lp.y));
+                        const uint64_t xb = ffma2(pack_f32x2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack_f32x2(lp.z, lp.w));
+                        float a0, a1, b0, b1;
+                        unpack_f32x2(xa, a0, a1);
+                        unpack_f32x2(xb, b0, b1);
+                        acc[0] = fadd2(acc[0], pack_f32x2(fast_exp2(a0), fast_exp2(a1)));
+                        acc[1] = fadd2(acc[1], pack_f32x2(fast_exp2(b0), fast_exp2(b1)));
                     }
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bar.acc_empty[ab]);
-                const int key = kt * KT + key_in_tile;
-                if (key < P.Nk) crow[key] = __float2bfloat16(acc0 + acc1);
+                float s0, s1, s2, s3;
+                unpack_f32x2(acc[0], s0, s1);
+                unpack_f32x2(acc[1], s2, s3);
+                const float part = (s0 + s1) + (s2 + s3);
+                // the two threads of a key meet on a 64-thread named barrier per lane quadrant
+                if (grp == 1) {
+                    s_part[ab][key_in_tile] = part;
+                    named_bar_sync(2 + wq, 64);
+                } else {
+                    named_bar_sync(2 + wq, 64);
+                    const int key = kt * KT + key_in_tile;
+                    if (key < P.Nk) crow[key] = __float2bfloat16(part + s_part[ab][key_in_tile]);
+                }
             }
         }
     }

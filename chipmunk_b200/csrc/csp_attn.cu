@@ -34,12 +34,22 @@ namespace attn {
 
 constexpr int NSLOT = 5;            // 32 KB K/V slots
 constexpr int SLOT_BYTES = KT * D * 2;
-constexpr int Q_HALF_BYTES = QG * 128;          // one 64-wide d-half of the Q tile
-constexpr int Q_BYTES = 2 * Q_HALF_BYTES;       // 49152
-constexpr int SMEM_BYTES = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
-
-constexpr int NUM_THREADS = 384;    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
-constexpr int WARP_MMA = 6;
+// Per-variant geometry.  The column-sparse kernel works on the reference's 192-query index groups (block 1 is half
+// empty: an M=128 MMA for 64 rows).  Dense attention has no index groups, so its tiles are 256 queries = two FULL
+// M=128 blocks: a third more rows for the same tensor time, 8 softmax warps (2 per SM sub-partition).
+template <bool DENSE> struct Geo {
+    static constexpr int QROWS = DENSE ? 256 : QG;               // query rows per tile
+    static constexpr int Q_HALF_BYTES = QROWS * 128;             // one 64-wide d-half of the Q tile
+    static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB / 64 KB
+    static constexpr int SMEM_BYTES = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
+    // sparse: warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
+    // dense : warps 0-3 softmax blk0 | 4-7 softmax blk1 | 8-11 producers | 12 MMA, 13-15 idle
+    static constexpr int NUM_THREADS = DENSE ? 512 : 384;
+    static constexpr int WARP_MMA = DENSE ? 12 : 6;
+    static constexpr int NUM_SOFTMAX_WARPS = DENSE ? 8 : 6;
+    static constexpr int REG_SOFTMAX = DENSE ? 200 : 208;        // setmaxnreg budgets: 64 K registers per SM
+    static constexpr int REG_OTHER = DENSE ? 56 : 80;
+};
 constexpr int WARP_PROD0 = 8;
 constexpr int NUM_PROD = 128;
 
@@ -80,7 +90,9 @@ __device__ __forceinline__ int tile_count(const Params& P, int tile, bool dense)
 
 // ------------------------------------------------------------------------------------------
 template <bool DENSE>
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
+__global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const Params P) {
+    using GEO = Geo<DENSE>;
+    constexpr int QROWS = GEO::QROWS, Q_HALF_BYTES = GEO::Q_HALF_BYTES, Q_BYTES = GEO::Q_BYTES, WARP_MMA = GEO::WARP_MMA;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
     __shared__ uint32_t tmem_base_s;
@@ -95,7 +107,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         mbar_init(&bar.q_empty, 1);
         for (int i = 0; i < NSLOT; i++) { mbar_init(&bar.kv_full[i], NUM_PROD); mbar_init(&bar.kv_empty[i], 1); }
         mbar_init(&bar.s_full[0], 1);  mbar_init(&bar.s_full[1], 1);
-        mbar_init(&bar.p_full[0], 128); mbar_init(&bar.p_full[1], 64);
+        mbar_init(&bar.p_full[0], 128); mbar_init(&bar.p_full[1], QROWS - 128);
         mbar_init(&bar.o_full[0], 1);  mbar_init(&bar.o_full[1], 1);
         fence_mbar_init();
     }
@@ -106,8 +118,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
     const uint32_t tm = tmem_base_s;
 
     // =========================================================================== producers
-    if (warp >= WARP_PROD0) {
-        setmaxnreg_dec<80>();
+    if (warp >= WARP_PROD0 && warp < WARP_PROD0 + 4) {
+        setmaxnreg_dec<GEO::REG_OTHER>();
         const int pt = tid - WARP_PROD0 * 32;       // 0..127
         const int chunk = pt & 15;                  // 16-byte chunk of the 256-byte row
         const int rsub = pt >> 4;                   // 0..7
@@ -124,9 +136,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
             {
                 const __nv_bfloat16* qb = P.q + b * P.qs[0] + h * P.qs[1];
 #pragma unroll 4
-                for (int i = 0; i < QG / 8; i++) {
+                for (int i = 0; i < QROWS / 8; i++) {
                     const int r = rsub + 8 * i;
-                    const int row = g * QG + r;
+                    const int row = g * QROWS + r;
                     const bool ok = row < P.Nq;
                     const __nv_bfloat16* src = qb + (ok ? row : 0) * P.qs[2] + chunk * 8;
                     cp_async_16_zfill(sQ + half_off * Q_HALF_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
-        setmaxnreg_inc<208>();
+        if (DENSE) setmaxnreg_dec<GEO::REG_OTHER>(); else setmaxnreg_inc<GEO::REG_SOFTMAX>();   // warpgroup-wide: sparse shares WG1 with softmax warps
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
         const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
@@ -276,8 +288,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         }
     }
     // =========================================================================== softmax + epilogue
-    else if (warp < 6) {
-        setmaxnreg_inc<208>();
+    else if (warp < GEO::NUM_SOFTMAX_WARPS) {
+        setmaxnreg_inc<GEO::REG_SOFTMAX>();
         const int blk = warp >> 2;                         // 0: rows 0-127, 1: rows 128-191
         const int r_in_tile = blk * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             const int count = tile_count(P, tile, DENSE);
             const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
-            const int row = g * QG + r_in_tile;
+            const int row = g * QROWS + r_in_tile;
             const bool row_ok = row < P.Nq;
             __nv_bfloat16* orow = P.o + b * P.os[0] + h * P.os[1] + (int64_t)(row_ok ? row : 0) * P.os[2];
             if (count <= 0) {
@@ -381,7 +393,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_kernel(const Params P) {
         }
     }
     else {
-        setmaxnreg_inc<208>();      // warp 7: idle, but setmaxnreg is warpgroup-wide
+        // idle warps: setmaxnreg is warpgroup-wide (sparse: warp 7 in the softmax group; dense: warps 13-15 with the MMA warp)
+        if (DENSE) setmaxnreg_dec<GEO::REG_OTHER>(); else setmaxnreg_inc<GEO::REG_SOFTMAX>();
     }
 
     tc_fence_before_sync();
@@ -403,12 +416,12 @@ static int launch_attn(Params& P, cudaStream_t stream) {
     static bool configured = false;
     auto kern = attn_kernel<DENSE>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<DENSE>::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(P);
+    kern<<<grid, Geo<DENSE>::NUM_THREADS, Geo<DENSE>::SMEM_BYTES, stream>>>(P);
     return (int)cudaGetLastError();
 }
 
@@ -508,7 +521,7 @@ extern "C" int cm_dense_attn(const void* q, const void* k, const void* v, void* 
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
     P.o = (__nv_bfloat16*)o;
     P.indices = nullptr; P.counts = nullptr; P.l = l;
-    P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
+    P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + Geo<true>::QROWS - 1) / Geo<true>::QROWS;
     const int64_t qst[3] = {(int64_t)H * Nq * D, (int64_t)Nq * D, D};
     const int64_t kst[3] = {(int64_t)H * Nk * D, (int64_t)Nk * D, D};
     for (int i = 0; i < 3; i++) { P.qs[i] = qst[i]; P.os[i] = qst[i]; P.ks[i] = kst[i]; P.vs[i] = kst[i]; }
