@@ -391,7 +391,15 @@ def c3_attention(dev, world, rank):
         return parallel.sparse_attention_head_parallel(q, k, v, o, idx, cnt, hl * world)
 
     for _ in range(2):
-        layer()
+        full = layer()
+    # self-check outside the timed region: this rank's slice of the gathered layer is what its kernel wrote,
+    # and every other slice arrived (finite, non-zero)
+    from chipmunk_b200 import torch_ops as T
+    mine = T.csp_attn_add(q, k, v, o, idx, cnt, 1)
+    assert torch.equal(full[:, rank * hl:(rank + 1) * hl], mine), "head-parallel gather: own slice differs"
+    assert bool(torch.isfinite(full.float()).all()) and all(
+        float(full[:, r * hl:(r + 1) * hl].float().abs().sum()) > 0 for r in range(world)), "head-parallel gather: missing slice"
+    del mine, full
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
