@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchipmunk_b200.so")
+# CHIPMUNK_B200_LIB: development override for same-box A/B timing of two builds (never a fallback: it must exist)
+LIB_PATH = os.environ.get("CHIPMUNK_B200_LIB") or os.path.join(_HERE, "libchipmunk_b200.so")
 
 CM_BF16, CM_F16, CM_F32 = 0, 1, 2
 _DTYPE_TAG = {torch.bfloat16: CM_BF16, torch.float16: CM_F16, torch.float32: CM_F32}

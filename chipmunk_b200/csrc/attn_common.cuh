@@ -90,6 +90,53 @@ __device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid
 }
 
 
+// A step with at most 32 valid key columns (the 16-column tail that a count = k*112 or k*128+16 list ends with):
+// one 32-column chunk instead of four.  The step sits on the tile's critical chain like every other one, and at
+// FLUX sizes (7 steps per tile) a full-width pass over a 16-column tail is ~4 % of the kernel.
+__device__ __forceinline__ void softmax_step_narrow(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref, float& l_sum) {
+    uint32_t s[32];
+    tmem_ld32(tS, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j++) s[j] = j < valid ? s[j] : 0xff800000u;
+    float mx = __uint_as_float(s[0]);
+#pragma unroll
+    for (int j = 1; j < 31; j += 2) mx = fmax3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+    const float m_tile = fmaxf(mx, __uint_as_float(s[31]));
+    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
+    if (__any_sync(0xffffffffu, need)) {
+        float alpha = 1.f;
+        if (need) {
+            alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);
+            m_ref = m_tile;
+            l_sum *= alpha;
+        }
+        if (kk > 0) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tO + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+                tmem_st_32x32b_x32(tO + c0, r);
+            }
+        }
+    }
+    const float neg_m = -m_ref * SCALE_LOG2;
+    float acc = 0.f;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), SCALE_LOG2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), SCALE_LOG2, neg_m));
+        acc += p0 + p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+    }
+    tmem_st_32x32b_x16(tS, pk);
+    l_sum += acc;
+}
+
 // Half-row variant: TWO threads (same TMEM lane, two warps of the same lane quadrant) share a query row,
 // thread `hf` owning key columns [64 hf, 64 hf + 64) of the step and head dims [64 hf, 64 hf + 64) of O.
 // One warp per SM sub-partition cannot hide the exp2/convert latencies of a 128-column row; two can.

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                 tc_fence_after_sync();
                 if (P.dbg & 4) { l_sum = 1.f; }
                 else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
+                else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum);
                 else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum);
                 tmem_st_wait();
                 tc_fence_before_sync();

@@ -1,1 +1,4 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_n2.json
+for rep in 1 2; do for L in A B; do echo lib$L
+CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/lib$L.so timeout 200 python tools/quick_attn.py 4608 784 1 24 20 2>&1 | head -1
+CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/lib$L.so timeout 200 python tools/quick_attn.py 16384 2944 1 24 10 2>&1 | head -1
+done; done
