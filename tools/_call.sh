@@ -1,4 +1,5 @@
-for rep in 1 2; do for L in A B; do echo lib$L
-CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/lib$L.so timeout 200 python tools/quick_attn.py 16384 2944 1 24 10 2>&1 | head -1
-CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/lib$L.so timeout 200 python tools/quick_mlp.py 4608 12288 3840 2>&1 | head -1
-done; done
+mkdir -p gpurun_out
+for n in 4 8; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 2>&1 | grep '^{' | tail -1 > gpurun_out/bench_n$n.json
+cut -c1-300 gpurun_out/bench_n$n.json
+done
