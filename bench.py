@@ -412,6 +412,30 @@ def c3_attention(dev, world, rank):
     t_attn = _time(lambda: torch.ops.chipmunk.csp_attn(q, k, v, o, idx, cnt, 1), 3, warm=1)
     res.update({"layer_ms_max_over_ranks": round(float(t.item()), 3), "attn_only_ms_this_rank": round(t_attn, 3),
                 "allgather_bytes_per_rank": o.numel() * 2, "collective": "1x ncclAllGather of O per layer"})
+    # the same layer with the all-gather fused into the kernel epilogue (NVLS multicast stores, parallel.py)
+    try:
+        def layer_fused():
+            return parallel.sparse_attention_head_parallel_fused(q, k, v, o, idx, cnt, hl * world)
+
+        full_f = layer_fused()
+        full_n = layer()
+        dist.barrier(); torch.cuda.synchronize()
+        assert torch.equal(full_f, full_n), "fused multicast gather differs from the NCCL all-gather"
+        del full_n
+        for _ in range(2):
+            layer_fused()
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            layer_fused()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        tf = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        res["fused_multicast_layer_ms_max_over_ranks"] = round(float(tf.item()), 3)
+    except Exception as e:  # noqa: BLE001  (no NVLS on this box: the NCCL number above stands)
+        res["fused_multicast_layer_ms_max_over_ranks"] = None
+        res["fused_multicast_error"] = repr(e)[:200]
     return res
 
 

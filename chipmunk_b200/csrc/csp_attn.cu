@@ -71,6 +71,7 @@ struct Params {
     float o_scale;
     int accumulate;
     int wide;                    // o (and cache) rows are 32-byte aligned: the epilogue moves full sectors per access
+    int64_t mc_delta;            // != 0: o lives in a symmetric buffer; rows are stored to (o + mc_delta bytes), its NVLS multicast alias
     int num_tiles;
     int dbg;                     // CM_DEBUG_FLAGS: timing experiments only (results are wrong when set)
 };
@@ -308,7 +309,11 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                     if (row_ok) {
                         const uint4* crow = reinterpret_cast<const uint4*>(P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)row * P.cs[2]);
 #pragma unroll
-                        for (int c = 0; c < 16; c++) reinterpret_cast<uint4*>(orow)[c] = __ldg(crow + c);
+                        for (int c = 0; c < 16; c++) {
+                            const uint4 t = __ldg(crow + c);
+                            if (P.mc_delta != 0) multimem_st_v4(reinterpret_cast<char*>(orow) + P.mc_delta + c * 16, t.x, t.y, t.z, t.w);
+                            else reinterpret_cast<uint4*>(orow)[c] = t;
+                        }
                     }
                 } else if (!P.accumulate && row_ok) {
 #pragma unroll
@@ -380,6 +385,12 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
 #pragma unroll
                         for (int c = 0; c < 8; c++)
                             red_add_bf16x8(orow + hf * 64 + c * 8, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                    } else if (P.mc_delta != 0) {
+                        // fused all-gather: ONE multicast store per 16 bytes puts the row into every GPU's copy of the
+                        // layer output through the NVSwitch while the other tiles are still being computed
+                        char* mrow = reinterpret_cast<char*>(orow + hf * 64) + P.mc_delta;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) multimem_st_v4(mrow + c * 16, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
                     } else if (P.wide) {
 #pragma unroll
                         for (int c = 0; c < 4; c++) st_global_v8(orow + hf * 64 + c * 16, w + 8 * c);
@@ -444,7 +455,8 @@ int launch(const void* q, const void* k, const void* v, void* o, float* l, const
 static int csp_attn_impl(const void* q, const void* k, const void* v, const void* cache, void* o, const int32_t* indices,
                          const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
                          const int64_t k_strides[3], const int64_t v_strides[3], const int64_t c_strides[3],
-                         const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
+                         const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, int accumulate, void* stream,
+                         int64_t mc_delta = 0) {
     if (B < 0 || H < 0 || Nq < 0 || Nk <= 0 || idx_row_stride <= 0) return CM_EINVAL;
     if (o_scale != 1 && o_scale != -1) return CM_EINVAL;
     if ((int64_t)B * H * Nq == 0) return CM_OK;
@@ -480,6 +492,8 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
         return (reinterpret_cast<uintptr_t>(p) & 31) == 0 && st[0] % 16 == 0 && st[1] % 16 == 0 && st[2] % 16 == 0;
     };
     P.wide = wide_ok(o, o_strides) && (!cache || wide_ok(cache, c_strides)) ? 1 : 0;
+    if (mc_delta != 0 && (!cache || (mc_delta & 15))) return CM_EINVAL;
+    P.mc_delta = mc_delta;
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
@@ -493,6 +507,16 @@ extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o,
                            int64_t idx_row_stride, int o_scale, int accumulate, void* stream) {
     return csp_attn_impl(q, k, v, nullptr, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, nullptr,
                          o_strides, idx_row_stride, o_scale, accumulate, stream);
+}
+
+extern "C" int cm_csp_attn_add_bcast(const void* q, const void* k, const void* v, const void* cache, void* o_local,
+                                     int64_t multicast_delta_bytes, const int32_t* indices, const int32_t* counts, int B,
+                                     int H, int Nq, int Nk, const int64_t q_strides[3], const int64_t k_strides[3],
+                                     const int64_t v_strides[3], const int64_t cache_strides[3],
+                                     const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, void* stream) {
+    if (!cache || !cache_strides || multicast_delta_bytes == 0) return CM_EINVAL;
+    return csp_attn_impl(q, k, v, cache, o_local, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides,
+                         cache_strides, o_strides, idx_row_stride, o_scale, 0, stream, multicast_delta_bytes);
 }
 
 extern "C" int cm_csp_attn_add(const void* q, const void* k, const void* v, const void* cache, void* o,

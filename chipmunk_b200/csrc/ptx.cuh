@@ -198,6 +198,13 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+// 16-byte store to an NVLS multicast address: the NVSwitch replicates it into the same offset of every GPU of
+// the multicast group (the writer included).
+__device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(mc_ptr), "f"(__uint_as_float(a)),
+                 "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(addr) : "memory");

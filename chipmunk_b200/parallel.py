@@ -50,6 +50,50 @@ def all_gather_heads(o_local: torch.Tensor, num_heads: int, group=None) -> torch
     return torch.cat(parts, dim=1)
 
 
+# ---------------------------------------------------------------------------------------------------
+# Fused compute + all-gather over NVSwitch multicast (NVLS).
+#
+# The layer output lives in a SYMMETRIC buffer [world, B, h_local, N, D] (torch symmetric memory: the same
+# allocation on every GPU of the NVSwitch domain, mapped into each other's address space, plus one multicast
+# address that aliases all copies).  Each rank's attention kernel stores its rows ONCE, with `multimem.st`, to the
+# multicast alias of its own slice `[rank]`: the switch replicates every 16-byte store into all GPUs' buffers while
+# the rank's remaining tiles are still being computed, so the gather costs no extra pass over O and no separate
+# collective -- only a device-side barrier when the kernels are done.  This is what replaces the reference's two
+# all_to_all + all_gather per attention (hyvideo/modules/head_parallel.py:42-115) on B200.
+_SYMM = {}
+
+
+def _symm_buffer(shape, dtype, device, group):
+    import torch.distributed._symmetric_memory as symm
+
+    key = (tuple(shape), dtype, device.index, id(group))
+    if key not in _SYMM:
+        buf = symm.empty(*shape, dtype=dtype, device=device)
+        hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        if not getattr(hdl, "multicast_ptr", 0):
+            raise RuntimeError("NVLS multicast is not available on this system: use sparse_attention_head_parallel(fused=False)")
+        _SYMM[key] = (buf, hdl)
+    return _SYMM[key]
+
+
+def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
+    """One sparse attention step, heads sharded over the ranks of `group` (num_heads % world == 0), with the
+    all-gather of O fused into the kernel's epilogue (NVLS multicast stores).  Returns the full [B, H, N, D]
+    output as a view of the symmetric buffer: it stays valid until the next call with the same shape."""
+    from . import torch_ops as _t
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, h_local, N, D = q.shape
+    if num_heads != h_local * world:
+        raise RuntimeError("fused head-parallel attention needs num_heads == world_size * local heads")
+    buf, hdl = _symm_buffer((world, B, h_local, N, D), q.dtype, q.device, group)
+    hdl.barrier(channel=0)                       # every rank has consumed the previous contents of the buffer
+    mc_delta = int(hdl.multicast_ptr) - int(hdl.buffer_ptrs[rank])
+    _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1, out=buf[rank], multicast_delta=mc_delta)
+    hdl.barrier(channel=1)                       # every rank's kernel has finished: all slices are everywhere
+    return buf.permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
+
+
 def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
     """One sparse attention step with heads sharded over the ranks of `group`.
     q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output."""

@@ -72,6 +72,21 @@ int cm_csp_attn_add(const void* q, const void* k, const void* v, const void* cac
                     const int64_t v_strides[3], const int64_t cache_strides[3], const int64_t o_strides[3],
                     int64_t idx_row_stride, int o_scale, void* stream);
 
+/* cm_csp_attn_add fused with the head-parallel all-gather of O (replaces the two all_to_all + all_gather of
+ * examples/hunyuan/hyvideo/modules/head_parallel.py:42-115 for the sparse steps).  `o_local` is this GPU's slice of a
+ * SYMMETRIC buffer (same layout on every GPU of one NVSwitch domain) and `multicast_delta_bytes` the distance from
+ * that buffer's local address to its NVLS multicast alias: every output row is written once, with multimem.st, and
+ * the switch replicates it into all GPUs' copies while the remaining tiles are still being computed.  The caller
+ * owns the cross-GPU barrier after the kernel (and before the buffer is overwritten again).
+ */
+int cm_csp_attn_add_bcast(const void* q, const void* k, const void* v, const void* cache, void* o_local,
+                          int64_t multicast_delta_bytes,
+                          const int32_t* indices, const int32_t* counts,
+                          int B, int H, int Nq, int Nk,
+                          const int64_t q_strides[3], const int64_t k_strides[3],
+                          const int64_t v_strides[3], const int64_t cache_strides[3], const int64_t o_strides[3],
+                          int64_t idx_row_stride, int o_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Dense attention with the statistics the sparse steps need.
  * Replaces chipmunk::dense_attn        (csrc/attn/dense_attn.cu:246-371, schema chipmunk.cpp:54)
