@@ -388,7 +388,7 @@ def c3_attention(dev, world, rank):
 
     def layer():
         # csp_attn_add on this rank's heads, written into the gather buffer + ONE (in-place) all-gather of O
-        return parallel.sparse_attention_head_parallel(q, k, v, o, idx, cnt, hl * world)
+        return parallel.sparse_attention_head_parallel(q, k, v, o, idx, cnt, hl * world, fused=False)
 
     for _ in range(2):
         full = layer()

@@ -378,19 +378,42 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                             w[8 * c + j] = pack_bf16x2(bf16_lo(cv[c][j]) + bf16_lo(w[8 * c + j]), bf16_hi(cv[c][j]) + bf16_hi(w[8 * c + j]));
                     if (hf == 0) load_cache_half(1);
                 }
-                if (row_ok) {
+                if (P.mc_delta != 0) {
+                    // Fused all-gather: the rows go to the NVLS multicast alias of the symmetric output buffer, and the
+                    // NVSwitch replicates them into every GPU while the other tiles are still being computed.  A
+                    // row-per-thread store pattern would put 16-byte packets on NVLink (packet-rate-bound: measured 1.7x
+                    // SLOWER than a separate NCCL all-gather at 8 GPUs), so each group of 8 lanes first transposes its
+                    // 8 rows x 8 pieces of 16 bytes with three butterfly shuffle stages: store j of a group then
+                    // writes 128 CONTIGUOUS bytes of row 8g + j.
+                    const int t8 = lane & 7;
+#pragma unroll
+                    for (int m = 4; m >= 1; m >>= 1) {
+                        const bool up = (t8 & m) != 0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            if (j & m) continue;
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const uint32_t send = up ? w[4 * j + e] : w[4 * (j | m) + e];
+                                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, m);
+                                if (up) w[4 * j + e] = recv; else w[4 * (j | m) + e] = recv;
+                            }
+                        }
+                    }
+                    // w[4j .. 4j+3] now holds piece t8 of the row owned by lane (lane & ~7) + j
+                    const int row0 = row - t8;                      // first row of this 8-lane group
+                    char* gbase = reinterpret_cast<char*>(P.o + b * P.os[0] + h * P.os[1]) + P.mc_delta + hf * 128 + t8 * 16;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (row0 + j < P.Nq)
+                            multimem_st_v4(gbase + (int64_t)(row0 + j) * P.os[2] * 2, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                } else if (row_ok) {
                     if (!fused && P.accumulate) {
                         // in-place delta add-back (csp_attn): o = bf16(o + delta) as 16-byte reductions at the L2 (the
                         // reference uses a TMA reduce-add, csp_attn.cu:300)
 #pragma unroll
                         for (int c = 0; c < 8; c++)
                             red_add_bf16x8(orow + hf * 64 + c * 8, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-                    } else if (P.mc_delta != 0) {
-                        // fused all-gather: ONE multicast store per 16 bytes puts the row into every GPU's copy of the
-                        // layer output through the NVSwitch while the other tiles are still being computed
-                        char* mrow = reinterpret_cast<char*>(orow + hf * 64) + P.mc_delta;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) multimem_st_v4(mrow + c * 16, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
                     } else if (P.wide) {
 #pragma unroll
                         for (int c = 0; c < 4; c++) st_global_v8(orow + hf * 64 + c * 16, w + 8 * c);

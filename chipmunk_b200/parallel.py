@@ -94,10 +94,20 @@ def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_
     return buf.permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
 
 
-def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
+def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads: int, group=None, fused=None) -> torch.Tensor:
     """One sparse attention step with heads sharded over the ranks of `group`.
-    q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output."""
+    q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output.
+    fused=None: use the multicast-fused kernel when NVLS symmetric memory is available (8 GPUs, 720p layer:
+    1.75 ms vs 2.74 ms), else the in-place NCCL all-gather; fused=False forces the NCCL path."""
     from . import torch_ops as _t
+
+    if fused is not False and dist.is_initialized() and dist.get_world_size(group) > 1 \
+            and num_heads == q.shape[1] * dist.get_world_size(group) and q.is_cuda:
+        try:
+            return sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads, group)
+        except RuntimeError:
+            if fused:
+                raise
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     B, h_local, N, D = q.shape
