@@ -67,7 +67,8 @@ def main():
             ks = bench["kernels"]
             tb = sum(k["us"] for k in ks.values())
             f.write("bench.py CUDA-event shares: " + ", ".join(f"{n} {100 * k['us'] / tb:.1f}%" for n, k in ks.items()) + "\n")
-    for src, dst in (("p_bench_n1.json", f"{tag}_bench_n1.json"), ("p_bench_ref.json", f"{tag}_bench_reference_arm.json")):
+    for src, dst in (("p_bench_n1.json", f"{tag}_bench_n1.json"), ("p_bench_ref.json", f"{tag}_bench_reference_arm.json"),
+                     ("p_sweep.jsonl", f"{tag}_sweep.jsonl"), ("p_sample_schedule.json", f"{tag}_sample_schedule.json")):
         if os.path.exists(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
