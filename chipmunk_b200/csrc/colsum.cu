@@ -25,7 +25,31 @@ namespace cm {
 namespace attn {
 
 namespace cs {
+#ifndef CM_COLSUM_POLY
+#define CM_COLSUM_POLY 2      // every CM_COLSUM_POLY-th group of 4 scores is exponentiated on the FMA pipe (0: all on the MUFU)
+#endif
 constexpr int D = 128, QG = 192, KT = 128;
+
+// exp2 of two fp32 on the FMA / ALU pipes: x = n + f (round to nearest with the 1.5*2^23 trick), 2^f by a degree-3
+// Chebyshev fit on [-0.5, 0.5] (relative error 1.0e-4; the sums feed a top-k selection and are rounded to bf16),
+// 2^n added into the exponent field.  This kernel IS MUFU-throughput-bound (two exp warps per sub-partition and
+// nothing else on the FMA pipe), unlike the attention softmax where the polynomial costs what the MUFU it replaces costs.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x) {
+    float x0, x1;
+    unpack_f32x2(x, x0, x1);
+    const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t t = fadd2(xc, pack_f32x2(12582912.f, 12582912.f));
+    const uint64_t n = fadd2(t, pack_f32x2(-12582912.f, -12582912.f));
+    const uint64_t f = ffma2(n, pack_f32x2(-1.f, -1.f), xc);
+    uint64_t p = ffma2(f, pack_f32x2(0.0559220356f, 0.0559220356f), pack_f32x2(0.2426400828f, 0.2426400828f));
+    p = ffma2(p, f, pack_f32x2(0.6931210340f, 0.6931210340f));
+    p = ffma2(p, f, pack_f32x2(0.9999244815f, 0.9999244815f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(p, q0, q1);
+    return pack_f32x2(__uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23)),
+                      __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23)));
+}
 constexpr int Q_BYTES = 2 * QG * 128;       // 49152: two 64-wide d-halves
 constexpr int K_BYTES = 2 * KT * 128;       // 32768
 constexpr int KSTAGES = 3;
@@ -162,7 +186,8 @@ colsum_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                         unpack_f32x2(xa, a0, a1);
                         unpack_f32x2(xb, b0, b1);
                         acc[0] = fadd2(acc[0], pack_f32x2(fast_exp2(a0), fast_exp2(a1)));
-                        acc[1] = fadd2(acc[1], pack_f32x2(fast_exp2(b0), fast_exp2(b1)));
+                        if (CM_COLSUM_POLY > 0 && ((j >> 2) % (CM_COLSUM_POLY > 0 ? CM_COLSUM_POLY : 1)) == 0) acc[1] = fadd2(acc[1], exp2_poly2(xb));
+                        else acc[1] = fadd2(acc[1], pack_f32x2(fast_exp2(b0), fast_exp2(b1)));
                     }
                 }
                 tc_fence_before_sync();

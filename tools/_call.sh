@@ -1,4 +1,4 @@
-mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 10 --warmup 3 2>&1 | grep '^{' | tail -1 > gpurun_out/bench_n8.json
-python -c "
-import json; d=json.load(open('gpurun_out/bench_n8.json')); print(d['value'], d['c3_hunyuan_attn'])"
+for L in P0 P1 P2 P0 P1 P2; do echo lib$L
+CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/lib$L.so timeout 200 python tools/quick_dense.py 2>&1 | tail -1
+done
+CHIPMUNK_B200_LIB=$PWD/chipmunk_b200/libP1.so timeout 300 python -m pytest tests/test_attn_gpu.py -m gpu -q -k colsum 2>&1 | tail -2
