@@ -16,8 +16,10 @@ through the public ops from pinned HOST buffers with the H2D/D2H copies inside t
 
 N > 1 GPUs (torchrun, one rank per GPU): every rank runs the step on its own sample (the path
 shards over independent samples without any collective: weak scaling).  The head-parallel mode of
-the reference's multi-GPU HunyuanVideo path (heads sharded, ONE NCCL all-gather of O) is measured
-on the 720p attention shape and reported in the `head_parallel_c3` object.
+the reference's multi-GPU HunyuanVideo path is measured on the 720p attention shape and reported in the
+`c3_hunyuan_attn` object, twice: heads sharded + ONE in-place NCCL all-gather of O, and the same layer with the
+gather fused into the attention epilogue (NVLS multicast stores into a symmetric buffer, chipmunk_b200/parallel.py);
+the two results are asserted bit-identical on every run.
 
 --impl reference times the reference's own CPU implementation of the path -- its pure-PyTorch
 dense branch (modules/attn.py:194, modules/mlp.py:34), restated in oracle/ -- on the host cores.
