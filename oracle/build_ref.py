@@ -9,8 +9,10 @@ kernels are arch-generic CUDA + CUB + cuRAND and compile unmodified for sm_100a:
     /root/reference/csrc/indexed_io/mask_to_indices.cu
     /root/reference/csrc/indexed_io/topk_indices.cu
     /root/reference/csrc/indexed_io/copy_indices.cu
+    /root/reference/csrc/indexed_io/scatter_add.cu
 
-(`scatter_add.cu` includes kittens.cuh and is left out.)  They are compiled straight from
+plus `scatter_add.cu` (needs the vendored ThunderKittens headers of the reference tree, no Hopper-only code is
+instantiated).  They are compiled straight from
 /root/reference (never copied into this repo) together with `oracle/ref_shim.cpp`, which registers them
 as `torch.ops.chipmunk_ref.*`.  Output goes to `oracle/_ref/` only: git-ignored, NOT gpurun-ignored, so
 the built library travels to the GPU box where `tests/test_ref_kernels_gpu.py` runs the reference kernels
@@ -30,7 +32,10 @@ REF = os.environ.get("CHIPMUNK_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libchipmunk_ref_indexed_io.so")
 SOURCES = [os.path.join(REF, "csrc", "indexed_io", f)
-           for f in ("mask_to_indices.cu", "topk_indices.cu", "copy_indices.cu")]
+           for f in ("mask_to_indices.cu", "topk_indices.cu", "copy_indices.cu", "scatter_add.cu")]
+# scatter_add.cu includes the reference's vendored ThunderKittens headers (header-only, in the reference tree) and
+# csrc/common; only its bulk reduce-add helper is instantiated, which is plain sm_90+ PTX and builds for sm_100a
+TK_INCLUDES = [os.path.join(REF, "submodules", "ThunderKittens", "include"), os.path.join(REF, "csrc", "common")]
 SHIM = os.path.join(HERE, "ref_shim.cpp")
 
 
@@ -51,7 +56,9 @@ def build(force: bool = False) -> str | None:
     inc = [f"-I{p}" for p in ce.include_paths("cuda")]
     import sysconfig
     inc.append(f"-I{sysconfig.get_paths()['include']}")
-    common = ["-std=c++17", "-O3", "-Xcompiler", "-fPIC", "-DTORCH_API_INCLUDE_EXTENSION_H",
+    inc += [f"-I{p}" for p in TK_INCLUDES]
+    # -std=c++20 / -DKITTENS_HOPPER: the reference's own flags (setup.py:91-103)
+    common = ["-std=c++20", "-O3", "-DKITTENS_HOPPER", "-Xcompiler", "-fPIC", "-DTORCH_API_INCLUDE_EXTENSION_H",
               "-D_GLIBCXX_USE_CXX11_ABI=1", *inc]
     cuflags = ["-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
                "--expt-extended-lambda", "-DNDEBUG", "--use_fast_math", "-DTORCH_COMPILE",   # setup.py:91-98
@@ -71,7 +78,7 @@ def build(force: bool = False) -> str | None:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr[-4000:]}")
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+    with cf.ThreadPoolExecutor(max_workers=5) as ex:
         objs = list(ex.map(cc, [*SOURCES, SHIM]))
     tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
     cmd = [nvcc, "-shared", "-o", LIB, *objs, f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",

@@ -1,7 +1,7 @@
 """GPU parity against the REFERENCE'S OWN index kernels.
 
 `oracle/build_ref.py` compiles /root/reference/csrc/indexed_io/{mask_to_indices,topk_indices,
-copy_indices}.cu unmodified for sm_100a into oracle/_ref/libchipmunk_ref_indexed_io.so (registered as
+copy_indices,scatter_add}.cu unmodified for sm_100a into oracle/_ref/libchipmunk_ref_indexed_io.so (registered as
 `torch.ops.chipmunk_ref.*`); the built library travels to the GPU box.  Here the real reference kernels
 and ours run on the same inputs:
 
@@ -10,7 +10,9 @@ and ours run on the same inputs:
 * topk_indices    — counts exact, kept-column SET exact (the reference's order is an atomicInc race,
   topk_indices.cu:108-113), padding entries drawn from the rejected columns; with random_amount > 0 the
   kept set is still exact because the XORWOW seeding and the short-circuit draw order are reproduced;
-* copy_indices    — destination tensor bit-exact.
+* copy_indices    — destination tensor bit-exact;
+* csp_scatter_add — the activation cache after the scatter bit-exact (one bf16 add per element: the reference does it
+  with `cp.reduce.async.bulk ... add.bf16`, scatter_add.cu:50-64; ours in registers).
 
 The library is test infrastructure: nothing under chipmunk_b200/ loads it.
 """
@@ -131,3 +133,19 @@ def test_copy_indices_equals_reference_kernel(cm, ref, cuda, dtype):
     cm.ops.copy_indices(src, od, inds, cnts)
     torch.cuda.synchronize()
     assert torch.equal(od, rd)
+
+
+@pytest.mark.parametrize("M,F,counts", [(4, 1024, [256, 0, 1024, 16]), (6, 12288, [3840, 3840, 256, 2304, 12288, 512])])
+def test_scatter_add_equals_reference_kernel(cm, ref, cuda, M, F, counts):
+    g = torch.Generator().manual_seed(24 + F)
+    packed = torch.randn(1, M * 128, F, generator=g).to(torch.bfloat16).to(cuda)
+    pa = torch.randn(1, F, M * 128, generator=g).to(torch.bfloat16).to(cuda)
+    inds = torch.stack([torch.randperm(F, generator=g) for _ in range(M)]).int().reshape(1, M, F).to(cuda)
+    cnts = torch.tensor([counts], dtype=torch.int32, device=cuda)
+    r, o = pa.clone(), pa.clone()
+    ref.csp_scatter_add(packed, r, inds, cnts, M)           # one block per token block (its grid-stride loop reads counts[blockIdx.x])
+    torch.cuda.synchronize()
+    torch.ops.chipmunk.csp_scatter_add(packed, o, inds, cnts, 6)
+    torch.cuda.synchronize()
+    assert torch.equal(o, r), "scatter-add differs from the reference kernel"
+    assert not torch.equal(o, pa) or sum(counts) == 0
