@@ -149,3 +149,29 @@ def test_scatter_add_equals_reference_kernel(cm, ref, cuda, M, F, counts):
     torch.cuda.synchronize()
     assert torch.equal(o, r), "scatter-add differs from the reference kernel"
     assert not torch.equal(o, pa) or sum(counts) == 0
+
+
+def test_fused_cache_update_equals_mm1_plus_reference_scatter(cm, ref, cuda):
+    """chipmunk.ops.mlp fuses the activation-cache update into csp_mlp_mm1's epilogue; the reference runs its
+    scatter-add kernel on mm1's packed output (ops/mlp.py:64-92 -> csp_mlp_mm2_and_scatter_add).  Same inputs:
+    the cache after our fused mm1 must equal the cache after [our mm1 without update + the REFERENCE scatter kernel]."""
+    from chipmunk_b200 import torch_ops as T
+    g = torch.Generator().manual_seed(31)
+    M, K, F = 512, 256, 2048
+    bf = torch.bfloat16
+    x = torch.randn(M, K, generator=g).to(bf).to(cuda)
+    w1 = (torch.randn(F, K, generator=g) / K ** 0.5).to(bf).to(cuda)
+    b1 = (0.1 * torch.randn(F, generator=g)).to(bf).to(cuda)
+    pa = torch.randn(F, M, generator=g).to(bf).to(cuda)
+    idx = torch.stack([torch.randperm(F, generator=g) for _ in range(M // 128)]).int().to(cuda)
+    cnt = torch.tensor([512, 2048, 256, 1024], dtype=torch.int32, device=cuda)
+    c_a = torch.zeros(M, F, dtype=bf, device=cuda)
+    c_b = torch.zeros(M, F, dtype=bf, device=cuda)
+    pa_two_pass, pa_fused = pa.clone(), pa.clone()
+    T.mlp_mm1(x, w1, c_a, b1, pa_two_pass, idx, cnt, False)
+    ref.csp_scatter_add(c_a[None], pa_two_pass[None], idx[None], cnt[None], M // 128)
+    torch.cuda.synchronize()
+    T.mlp_mm1(x, w1, c_b, b1, pa_fused, idx, cnt, True)
+    torch.cuda.synchronize()
+    assert torch.equal(c_a, c_b)
+    assert torch.equal(pa_fused, pa_two_pass), "fused cache update differs from mm1 + the reference's scatter-add kernel"
