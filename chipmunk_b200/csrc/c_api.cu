@@ -1,20 +1,38 @@
 // ABI housekeeping: version, error strings, device queries.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
 
 namespace cm {
-static int g_sms = 0, g_major = 0;
-static void query() {
-    if (g_sms) return;
+constexpr int MAX_DEV = 64;
+static int g_sms[MAX_DEV] = {0}, g_major[MAX_DEV] = {0};
+static int query() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&g_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return -1;
+    if (!g_sms[dev]) {
+        cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_major[dev], cudaDevAttrComputeCapabilityMajor, dev);
+    }
+    return dev;
 }
-int sm_count() { query(); return g_sms > 0 ? g_sms : 148; }
-bool is_sm100() { query(); return g_major == 10; }
+int sm_count() { const int d = query(); return d >= 0 && g_sms[d] > 0 ? g_sms[d] : 148; }
+bool is_sm100() { const int d = query(); return d >= 0 && g_major[d] == 10; }
+int debug_flags() {
+    static const int flags = [] { const char* e = getenv("CM_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
+    return flags;
+}
+int opt_in_dynamic_smem(unsigned long long& mask, const void* func, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return 0;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+    return 0;
+}
 }  // namespace cm
 
 extern "C" int cm_abi_version(void) { return CM_ABI_VERSION; }

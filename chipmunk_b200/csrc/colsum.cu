@@ -223,12 +223,9 @@ int launch_colsum(const __nv_bfloat16* q, const __nv_bfloat16* k, const float* p
     if (rc) return rc;
     rc = encode_tmap_2d_bf16_sw128(&tk, k, (uint64_t)B * H * Nk, D, D * 2, KT);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;
+    rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(colsum_kernel), SMEM_BYTES);
+    if (rc) return rc;
     Params P{};
     P.p = p; P.cs = cs_out; P.BH = B * H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
     P.cs_stride = cs_row_stride;

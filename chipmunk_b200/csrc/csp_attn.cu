@@ -448,13 +448,10 @@ using namespace cm::attn;
 
 template <bool DENSE>
 static int launch_attn(Params& P, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured = 0;          // one per template instance
     auto kern = attn_kernel<DENSE>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<DENSE>::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    const int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), Geo<DENSE>::SMEM_BYTES);
+    if (rc) return rc;
     int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
     kern<<<grid, Geo<DENSE>::NUM_THREADS, Geo<DENSE>::SMEM_BYTES, stream>>>(P);
     return (int)cudaGetLastError();
@@ -520,7 +517,7 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
-    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
+    P.dbg = debug_flags();
     return launch_attn<false>(P, (cudaStream_t)stream);
 }
 

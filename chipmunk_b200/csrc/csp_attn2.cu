@@ -418,12 +418,8 @@ namespace cm { namespace attn2 {
 int launch(const void* q, const void* k, const void* v, void* o, const int32_t* indices, const int32_t* counts, int B,
            int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
            int64_t idx_row_stride, int o_scale, int accumulate, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;
+    if (int rc0 = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn2_kernel), SMEM_BYTES)) return rc0;
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v; P.o = (__nv_bfloat16*)o;
     P.indices = indices; P.counts = counts;
@@ -435,7 +431,7 @@ int launch(const void* q, const void* k, const void* v, void* o, const int32_t* 
     const int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
-    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
+    P.dbg = debug_flags();
     const int max_clusters = sm_count() / 2;
     const int clusters = P.num_tiles < max_clusters ? P.num_tiles : max_clusters;
     attn2_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(P);

@@ -392,12 +392,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn3_kernel(const Params P) {
 int launch(const void* q, const void* k, const void* v, void* o, float* l, const int32_t* indices, const int32_t* counts,
            int B, int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
            int64_t idx_row_stride, int o_scale, int accumulate, int dense, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static unsigned long long configured = 0;
+    if (int rc0 = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn3_kernel), SMEM_BYTES)) return rc0;
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v; P.o = (__nv_bfloat16*)o;
     P.l = l; P.indices = indices; P.counts = counts;

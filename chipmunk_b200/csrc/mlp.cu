@@ -453,13 +453,10 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 template <bool IS_MM2>
 static int launch_mlp(const CUtensorMap& tmap, const CUtensorMap& tmap_out, Params& P, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured = 0;          // one per template instance
     auto kern = mlp_kernel<IS_MM2>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IS_MM2 ? SMEM_MM2 : SMEM_MM1);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    const int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), IS_MM2 ? SMEM_MM2 : SMEM_MM1);
+    if (rc) return rc;
     const int tiles = P.n_mb * P.n_nb;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     kern<<<grid, NUM_THREADS, IS_MM2 ? SMEM_MM2 : SMEM_MM1, stream>>>(tmap, tmap_out, P);
@@ -481,7 +478,7 @@ extern "C" int cm_csp_mlp_mm1(const void* a, const void* w1, void* c, const void
     P.pa_T = (__nv_bfloat16*)pa_T; P.indices = indices; P.counts = counts;
     P.M = M; P.K = K; P.F = F; P.N = F; P.idx_stride = idx_stride; P.update_pa = update_pa ? 1 : 0;
     P.n_mb = M / BM; P.n_nb = (F + BN - 1) / BN;
-    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
+    P.dbg = debug_flags();
     CUtensorMap tmap_c;        // C [M, F] in boxes of 32 rows x 32 columns (the epilogue's TMA stores)
     rc = encode_tmap_2d_bf16(&tmap_c, c, (uint64_t)M, (uint64_t)F, (uint64_t)F * 2, 32, 32, 64);
     if (rc) return rc;
@@ -518,7 +515,7 @@ extern "C" int cm_csp_mlp_mm2(const void* packed, const void* w2_T, void* out, v
     P.indices = indices; P.counts = counts;
     P.M = M; P.K = F; P.F = F; P.N = N; P.idx_stride = idx_stride; P.update_pa = 0;
     P.n_mb = M / BM; P.n_nb = N / BN;
-    P.dbg = getenv("CM_DEBUG_FLAGS") ? atoi(getenv("CM_DEBUG_FLAGS")) : 0;
+    P.dbg = debug_flags();
     CUtensorMap tmap_out;      // out [M, N] in boxes of 32 rows x 64 columns (the epilogue's TMA reduce-add)
     rc = encode_tmap_2d_bf16_sw128(&tmap_out, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32);
     if (rc) return rc;
