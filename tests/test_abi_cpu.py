@@ -128,3 +128,24 @@ def test_storage_resident_mode(cm):
     with pytest.raises(ValueError):
         from chipmunk_b200.util import MaybeOffloadedTensor
         MaybeOffloadedTensor("attn.bogus", 0, torch.float32, "cpu")
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/chipmunk_b200.h must compile as C99 with nothing but <stdint.h>."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "chipmunk_b200.h")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_parallel_shards_and_fused_guard(cm):
+    """Host logic of the multi-GPU layer that needs no GPU: the fused (multicast) path refuses uneven head splits."""
+    import torch
+    from chipmunk_b200 import parallel
+    assert parallel.shard_heads(24, 8, 3) == (9, 12)
+    assert parallel.shard_heads(7, 2, 0) == (0, 4) and parallel.shard_heads(7, 2, 1) == (4, 7)
+    assert callable(parallel.sparse_attention_head_parallel_fused)
