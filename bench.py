@@ -430,14 +430,8 @@ def c3_attention(dev, world, rank):
         def layer_fused():
             return parallel.sparse_attention_head_parallel_fused(q, k, v, o, idx, cnt, hl * world)
 
-        # all ranks must agree that the symmetric buffer + NVLS multicast exist before anyone enters a device barrier
-        try:
-            parallel._symm_buffer((world, 1, hl, n, D), bf, dev, None)
-            ok = torch.ones(1, device=dev)
-        except Exception:  # noqa: BLE001
-            ok = torch.zeros(1, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) < 1:
+        # all ranks agree (all_reduce MIN inside) that the symmetric buffer + NVLS multicast exist before anyone enters a device barrier
+        if not parallel.fused_gather_available((world, 1, hl, n, D), bf, dev, None):
             raise RuntimeError("symmetric memory / NVLS multicast not available on every rank")
         full_f = layer_fused()
         full_n = layer()

@@ -46,9 +46,12 @@ def _headers_mtime() -> float:
     return max(os.path.getmtime(h) for h in hs if os.path.exists(h))
 
 
+EXTRA_FLAGS: list = []      # --debug-stages adds -DCM_DEBUG_STAGES (stage-isolation timing builds; never shipped)
+
+
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJ, src[:-3] + ".log")
     with open(log, "w") as f:
@@ -86,5 +89,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--debug-stages", action="store_true",
+                    help="compile the CM_DEBUG_FLAGS stage-isolation switches in (timing experiments; results are wrong when set)")
     a = ap.parse_args()
+    if a.debug_stages:
+        EXTRA_FLAGS.append("-DCM_DEBUG_STAGES")
+        a.force = True
     print(build(a.force, a.verbose))

@@ -20,8 +20,12 @@ static int query() {
 int sm_count() { const int d = query(); return d >= 0 && g_sms[d] > 0 ? g_sms[d] : 148; }
 bool is_sm100() { const int d = query(); return d >= 0 && g_major[d] == 10; }
 int debug_flags() {
+#ifdef CM_DEBUG_STAGES
     static const int flags = [] { const char* e = getenv("CM_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
     return flags;
+#else
+    return 0;
+#endif
 }
 int opt_in_dynamic_smem(unsigned long long& mask, const void* func, int bytes) {
     int dev = 0;

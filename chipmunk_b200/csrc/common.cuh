@@ -15,8 +15,15 @@ bool is_sm100();
 // Opt `func` into `bytes` of dynamic shared memory once per device; `mask` is the call site's static bit set
 // (one bit per device ordinal).  Returns 0 or a cudaError_t.
 int opt_in_dynamic_smem(unsigned long long& mask, const void* func, int bytes);
-// CM_DEBUG_FLAGS of the environment, read once per process.  Timing experiments only (stage isolation: skip the
-// gather / the MMAs / the softmax / the stores); kernels produce WRONG results when it is non-zero.
+// Stage-isolation timing switches (skip the gather / the MMAs / the softmax / the stores: results are WRONG).
+// They exist only in builds made with -DCM_DEBUG_STAGES (python chipmunk_b200/build.py --debug-stages); in the
+// shipped library CM_DBG() is the constant false, the branches are compiled out and debug_flags() returns 0
+// whatever the environment says.
 int debug_flags();
+#ifdef CM_DEBUG_STAGES
+#define CM_DBG(P, bit) (((P).dbg & (bit)) != 0)
+#else
+#define CM_DBG(P, bit) false
+#endif
 
 }  // namespace cm

@@ -73,7 +73,7 @@ struct Params {
     int wide;                    // o (and cache) rows are 32-byte aligned: the epilogue moves full sectors per access
     int64_t mc_delta;            // != 0: o lives in a symmetric buffer; rows are stored to (o + mc_delta bytes), its NVLS multicast alias
     int num_tiles;
-    int dbg;                     // CM_DEBUG_FLAGS: timing experiments only (results are wrong when set)
+    int dbg;                     // stage-isolation timing switches: only read in -DCM_DEBUG_STAGES builds (CM_DBG below)
 };
 
 struct __align__(8) Barriers {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                         const int r = rsub + 8 * i;
                         const bool ok = rowidx[i] >= 0;
                         const __nv_bfloat16* src = base + (int64_t)(ok ? rowidx[i] : 0) * rs;
-                        if (!(P.dbg & 1)) cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+                        if (!CM_DBG(P, 1)) cp_async_16_zfill(dst0 + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&bar.kv_full[slot]);
                     job++;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                 const uint32_t d = tm + (blk ? TM_S1 : TM_S0);
                 const uint64_t ad0 = desc_q + (uint64_t)(blk * ((128 * 128) >> 4));
                 const uint64_t bd0 = desc_k + (uint64_t)(slot * (SLOT_BYTES >> 4));
-                if (P.dbg & 2) return;
+                if (CM_DBG(P, 2)) return;
 #pragma unroll
                 for (int k16 = 0; k16 < D / 16; k16++) {
                     const uint64_t ad = ad0 + (uint64_t)((((k16 >> 2) * Q_HALF_BYTES) + (k16 & 3) * 32) >> 4);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                 const uint32_t d = tm + (blk ? TM_O1 : TM_O0);
                 const uint32_t a = tm + (blk ? TM_S1 : TM_S0);
                 const uint64_t bd0 = desc_v + (uint64_t)(slot * (SLOT_BYTES >> 4));
-                if (P.dbg & 2) return;
+                if (CM_DBG(P, 2)) return;
                 if (cols == KT) {
 #pragma unroll
                     for (int j = 0; j < KT / 16; j++) umma_ts(d, a + j * 8, bd0 + (uint64_t)(j * (2048 >> 4)), idesc_pv, (!first) || j > 0);
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
                 const int valid = min(KT, count - kk * KT);
                 mbar_wait(&bar.s_full[blk], sc & 1); sc++;
                 tc_fence_after_sync();
-                if (P.dbg & 4) { l_sum = 1.f; }
+                if (CM_DBG(P, 4)) { l_sum = 1.f; }
                 else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
                 else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum);
                 else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum);
@@ -460,18 +460,6 @@ static int launch_attn(Params& P, cudaStream_t stream) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool strides_ok(const int64_t s[3]) { return s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0; }
 
-namespace cm { namespace attn2 {
-int launch(const void* q, const void* k, const void* v, void* o, const int32_t* indices, const int32_t* counts, int B,
-           int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
-           int64_t idx_row_stride, int o_scale, int accumulate, cudaStream_t stream);
-} }
-
-namespace cm { namespace attn3 {
-int launch(const void* q, const void* k, const void* v, void* o, float* l, const int32_t* indices, const int32_t* counts,
-           int B, int H, int Nq, int Nk, const int64_t qs[3], const int64_t ks[3], const int64_t vs[3], const int64_t os[3],
-           int64_t idx_row_stride, int o_scale, int accumulate, int dense, cudaStream_t stream);
-} }
-
 static int csp_attn_impl(const void* q, const void* k, const void* v, const void* cache, void* o, const int32_t* indices,
                          const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
                          const int64_t k_strides[3], const int64_t v_strides[3], const int64_t c_strides[3],
@@ -486,15 +474,6 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
         return CM_EALIGN;
     if (cache && (!aligned16(cache) || !strides_ok(c_strides) || cache == o)) return cache == o ? CM_EINVAL : CM_EALIGN;
     if (!is_sm100()) return CM_EARCH;
-    // CM_ATTN_V2=1 selects the experimental CTA-pair kernel (csp_attn2.cu: correct, not yet faster)
-    static const bool use_v2 = getenv("CM_ATTN_V2") && atoi(getenv("CM_ATTN_V2")) != 0;
-    static const bool use_v3 = getenv("CM_ATTN_V3") && atoi(getenv("CM_ATTN_V3")) != 0;
-    if (use_v3 && !cache)
-        return cm::attn3::launch(q, k, v, o, nullptr, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
-                                 idx_row_stride, o_scale, accumulate, 0, (cudaStream_t)stream);
-    if (use_v2 && !cache)
-        return cm::attn2::launch(q, k, v, o, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides, o_strides,
-                                 idx_row_stride, o_scale, accumulate, (cudaStream_t)stream);
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
     P.o = (__nv_bfloat16*)o;

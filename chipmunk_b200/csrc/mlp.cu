@@ -55,7 +55,7 @@ struct Params {
     int64_t idx_stride;
     int update_pa;
     int n_mb, n_nb;            // tile grid
-    int dbg;                   // CM_DEBUG_FLAGS (timing experiments only; results are wrong when set)
+    int dbg;                   // stage-isolation timing switches: only read in -DCM_DEBUG_STAGES builds (CM_DBG)
 };
 
 struct __align__(8) Barriers {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const int r = r0 + 16 * i;
-                        if (((okm >> i) & 1u) && !(P.dbg & 1))
+                        if (((okm >> i) & 1u) && !CM_DBG(P, 1))
                             cp_async_16_hint(dst + r * 128 + ((chunk ^ (r & 7)) << 4), src[i] + ks * BK, pol_w);
                     }
                     cp_async_mbar_arrive_noinc(&bar.full[s]);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                             const int r = w + 4 * i;
                             int f = __shfl_sync(0xffffffffu, f_cur, i);
                             f = f >= P.F ? P.F - 1 : f;
-                            if (f >= 0 && !(P.dbg & 1)) cp_async_16_hint(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N, pol_w);
+                            if (f >= 0 && !CM_DBG(P, 1)) cp_async_16_hint(dst + r * 128 + (((chunk & 7) ^ (r & 7)) << 4), wb + (int64_t)f * P.N, pol_w);
                         }
                         cp_async_mbar_arrive_noinc(&bar.full[s]);
                         it++;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 for (int ks = 0; ks < ksteps; ks++, it++) {
                     const uint32_t s = it % STAGES;
                     mbar_wait(&bar.empty[s], ((it / STAGES) & 1) ^ 1);
-                    if (P.dbg & 2) { mbar_arrive(&bar.full[s]); continue; }
+                    if (CM_DBG(P, 2)) { mbar_arrive(&bar.full[s]); continue; }
                     mbar_arrive_expect_tx(&bar.full[s], A_BYTES);
                     tma_load_2d(sbase + s * STAGE_BYTES, &tmap_a, &bar.full[s], ks * BK, mb * BM);
                 }
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 if (elect_one()) {      // elect.sync: ptxas emits the UTCHMMAs back to back (a lane test costs a per-instruction ELECT loop)
                     const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
                     const int k16s = (ks == ksteps - 1 ? klast : BK) / 16;
-                    for (int k16 = 0; k16 < ((P.dbg & 4) ? 0 : k16s); k16++) {
+                    for (int k16 = 0; k16 < (CM_DBG(P, 4) ? 0 : k16s); k16++) {
                         const uint64_t ad = umma_smem_desc(sa + k16 * 32, 16, 1024);
                         const uint64_t bd = IS_MM2 ? umma_smem_desc(sb + k16 * 2048, BK * 128, 1024)
                                                    : umma_smem_desc(sb + k16 * 32, 16, 1024);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                 named_bar_sync(1, NUM_EPI);
             }
             const uint32_t tacc = tm + buf * BN + lane_off;
-            if (P.dbg & 8) {
+            if (CM_DBG(P, 8)) {
                 mbar_wait(&bar.acc_full[buf], (tcount >> 1) & 1);
             } else if constexpr (!IS_MM2) {
                 // The weight gather saturates the LSU / L1 path, so the epilogue keeps off it: per 32-column chunk a
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                             }
                         }
                     }
-                    if (P.dbg & 16) continue;
+                    if (CM_DBG(P, 16)) continue;
                     if (nvalid == 32) {
                         if (lane == 0) bulk_wait_read<0>();          // the previous box has left the staging buffer
                         __syncwarp();
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_kernel(const __grid_consta
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && !(P.dbg & 16)) {
+                    if (lane == 0 && !CM_DBG(P, 16)) {
                         tma_reduce_add_2d(&tmap_out, stg, nb * BN + c0, mb * BM + wq * 32);
                         bulk_commit();
                     }
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(const __nv_bfloat16* _
     __shared__ __nv_bfloat16 tile[BM][SC_COLS + 2];
     const int mb = blockIdx.y, c0 = blockIdx.x * SC_COLS;
     int cnt = counts[mb];
-    cnt = cnt > F ? F : cnt;
+    cnt = (cnt < 0 ? 0 : (cnt > F ? F : cnt)) & ~15;      // the same clamp + 16-column granularity as mlp_kernel::tile_shape
     if (c0 >= cnt) return;
     const int ncol = min(SC_COLS, cnt - c0);
     const int tid = threadIdx.x;

@@ -61,6 +61,11 @@ def all_gather_heads(o_local: torch.Tensor, num_heads: int, group=None) -> torch
 # collective -- only a device-side barrier when the kernels are done.  This is what replaces the reference's two
 # all_to_all + all_gather per attention (hyvideo/modules/head_parallel.py:42-115) on B200.
 _SYMM = {}
+_FUSED_OK = {}      # (group id, shape, dtype, device) -> bool, decided COLLECTIVELY once
+
+
+class NvlsUnavailable(RuntimeError):
+    """Symmetric memory / NVLS multicast cannot be used for this (group, shape) on this system."""
 
 
 def _symm_buffer(shape, dtype, device, group):
@@ -68,12 +73,32 @@ def _symm_buffer(shape, dtype, device, group):
 
     key = (tuple(shape), dtype, device.index, id(group))
     if key not in _SYMM:
-        buf = symm.empty(*shape, dtype=dtype, device=device)
-        hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        try:
+            buf = symm.empty(*shape, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        except Exception as e:  # noqa: BLE001  (allocator / rendezvous failures are "not available", nothing else is)
+            raise NvlsUnavailable(f"symmetric memory rendezvous failed: {e!r}") from e
         if not getattr(hdl, "multicast_ptr", 0):
-            raise RuntimeError("NVLS multicast is not available on this system: use sparse_attention_head_parallel(fused=False)")
+            raise NvlsUnavailable("NVLS multicast is not available on this system: use sparse_attention_head_parallel(fused=False)")
         _SYMM[key] = (buf, hdl)
     return _SYMM[key]
+
+
+def fused_gather_available(shape, dtype, device, group=None) -> bool:
+    """Whether EVERY rank of `group` can use the multicast-fused gather for this output shape.  The probe (symmetric
+    allocation + rendezvous + multicast pointer) runs once per (group, shape); the ranks then agree on the outcome
+    with an all_reduce(MIN), so that no rank can enter the device barriers of the fused path while another one falls
+    back to the NCCL all-gather (mismatched collectives = hang).  The decision is cached."""
+    key = (id(group), tuple(shape), dtype, device.index)
+    if key not in _FUSED_OK:
+        try:
+            _symm_buffer(shape, dtype, device, group)
+            ok = torch.ones(1, device=device, dtype=torch.int32)
+        except NvlsUnavailable:
+            ok = torch.zeros(1, device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        _FUSED_OK[key] = bool(int(ok.item()))
+    return _FUSED_OK[key]
 
 
 def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
@@ -103,11 +128,13 @@ def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads:
 
     if fused is not False and dist.is_initialized() and dist.get_world_size(group) > 1 \
             and num_heads == q.shape[1] * dist.get_world_size(group) and q.is_cuda:
-        try:
+        w = dist.get_world_size(group)
+        B_, hl_, N_, D_ = q.shape
+        # decided once per (group, shape) by ALL ranks together; kernel / argument errors of the fused call propagate
+        if fused_gather_available((w, B_, hl_, N_, D_), q.dtype, q.device, group):
             return sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads, group)
-        except RuntimeError:
-            if fused:
-                raise
+        if fused:
+            raise NvlsUnavailable("fused=True but symmetric memory / NVLS multicast is not available on every rank")
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     B, h_local, N, D = q.shape

@@ -112,9 +112,10 @@ class MaybeOffloadedTensor:
         dst = ring[self.layer_key]
         inp = _stream("load")
         inp.wait_stream(torch.cuda.current_stream())
+        inp.wait_stream(_stream("offload"))      # the previous offload() may still be writing this pinned buffer (D2H)
         with torch.cuda.stream(inp):
             dst.copy_(self.cpu_buf[key][: dst.numel()].view(shape), non_blocking=True)
-            dst.record_stream(_stream("offload"))
+        dst.record_stream(inp)                    # allocated on the current stream, written on the load stream
         return dst
 
     def load_async_wait(self) -> None:

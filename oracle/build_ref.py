@@ -39,11 +39,31 @@ TK_INCLUDES = [os.path.join(REF, "submodules", "ThunderKittens", "include"), os.
 SHIM = os.path.join(HERE, "ref_shim.cpp")
 
 
+# The reference's two Triton kernels (the ONLY mm2 implementation it has, and the fp8-capable mm1) are arch-portable:
+# they JIT for sm_100 on the GPU box.  They are staged -- byte-for-byte, by this recipe, into the git-ignored
+# oracle/_ref/triton_ref/ -- so that tests/test_ref_triton_gpu.py and bench.py's `reference_gpu` leg can import them
+# there (/root/reference does not exist on the GPU box; nothing of them enters the repo's history).
+TRITON_SOURCES = [os.path.join(REF, "src", "chipmunk", "triton", f) for f in ("csp_mlp_mm1.py", "csp_mlp_mm2.py")]
+TRITON_OUT = os.path.join(OUT, "triton_ref")
+
+
+def stage_triton(force: bool = False) -> str | None:
+    if not all(os.path.exists(s) for s in TRITON_SOURCES):
+        return TRITON_OUT if os.path.isdir(TRITON_OUT) else None
+    os.makedirs(TRITON_OUT, exist_ok=True)
+    for s in TRITON_SOURCES:
+        dst = os.path.join(TRITON_OUT, os.path.basename(s))
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(s):
+            shutil.copyfile(s, dst)
+    return TRITON_OUT
+
+
 def available() -> bool:
     return all(os.path.exists(s) for s in SOURCES)
 
 
 def build(force: bool = False) -> str | None:
+    stage_triton(force)
     if os.path.exists(LIB) and not force:
         return LIB
     if not available():
