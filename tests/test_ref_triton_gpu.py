@@ -63,11 +63,15 @@ def _problem(M, K, F, counts, seed, cuda):
     return x, w1, b1, w2t, pa, out, packed, idx, cnt
 
 
-def _ulp_close(a, b, what, max_ulps=2, frac_off=2e-2):
-    """bf16 results of the same fp32 value up to summation order: equal or adjacent bf16 values nearly everywhere."""
+def _ulp_close(a, b, what, mag=None, max_ulps=2, frac_off=2e-2):
+    """bf16 results of the same fp32 value up to summation order: equal or adjacent bf16 values nearly everywhere.
+    `mag`: magnitude of the operands of the final bf16 add (a result that cancels is only accurate to THEIR ulp)."""
     a32, b32 = a.float(), b.float()
     assert torch.isfinite(a32).all(), what
-    tol = max_ulps * 2.0 ** -8 * torch.maximum(a32.abs(), b32.abs()).clamp_min(2.0 ** -6)
+    scale = torch.maximum(a32.abs(), b32.abs())
+    if mag is not None:
+        scale = torch.maximum(scale, mag.float().to(scale.device))
+    tol = max_ulps * 2.0 ** -8 * scale.clamp_min(2.0 ** -6)
     bad = (a32 - b32).abs() > tol
     assert not bool(bad.any()), f"{what}: {int(bad.sum())} elements differ by more than {max_ulps} bf16 ulps"
     off = float((a != b).float().mean())
@@ -90,10 +94,11 @@ def test_mm2_matches_reference_triton_kernel(cm, oracle, cuda, ref_mm2, M, K, F,
     T.mlp_mm2(packed, w2t, ours, None, idx, cnt, False)
     torch.cuda.synchronize()
     assert not torch.equal(theirs, out)
-    _ulp_close(ours, theirs, "mm2 vs the reference Triton kernel")
+    mag = out.float().abs() + (theirs.float() - out.float()).abs()       # |out| + |bf16(acc)|
+    _ulp_close(ours, theirs, "mm2 vs the reference Triton kernel", mag)
     if M <= 512:      # and the CPU oracle's restatement is pinned by the same kernel
         ref = oracle.csp_mlp_mm2(packed.cpu(), w2t.cpu(), idx.cpu(), cnt.cpu(), out.cpu())
-        _ulp_close(theirs.cpu(), ref, "reference Triton mm2 vs the CPU oracle")
+        _ulp_close(theirs.cpu(), ref, "reference Triton mm2 vs the CPU oracle", mag.cpu())
 
 
 @pytest.mark.parametrize("M,K,F,counts", [
@@ -106,6 +111,10 @@ def test_mm1_and_cache_update_match_reference_triton_kernel(cm, oracle, cuda, re
     works on 128-column tiles (:91-92), so counts are multiples of 128 here."""
     x, w1, b1, w2t, pa, out, packed, idx, cnt = _problem(M, K, F, counts, 9 + M, cuda)
     one = torch.ones(1, device=cuda, dtype=torch.float32)
+    # The kernel is @triton.autotune'd over 8 configs and UPDATES the cache in place (csp_mlp_mm1.py:140), so the tuning
+    # runs of a first call compound on its arguments: tune on scratch copies first (the choice is cached per M, N, K).
+    ref_mm1.csp_mlp_mm1(x, w1, b1, idx, cnt, pa.clone(), torch.zeros(M, F, dtype=BF, device=cuda), one, one)
+    torch.cuda.synchronize()
     c_ref = torch.zeros(M, F, dtype=BF, device=cuda)
     pa_ref = pa.clone()
     # the wrapper reads `N, K = b.shape` and strides (b.stride(1), b.stride(0)) (csp_mlp_mm1.py:145-159): b is [F, K]
