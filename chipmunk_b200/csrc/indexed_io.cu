@@ -94,22 +94,120 @@ __global__ void __launch_bounds__(256) bitunpack_kernel(const uint8_t* __restric
 // The reference emits set columns in (c, i) order -- lane c of its single warp owns columns
 // c, c+32, ... (mask_to_indices.cu:47-68).  Thread (warp w, lane c) here owns class c of the
 // w-th slice of words; an exclusive scan over (c, w) gives every thread its output cursor.
+// The index list is assembled in SHARED memory (a scatter there costs bank conflicts, not DRAM
+// sectors) and leaves the SM as one coalesced run of 16-byte stores: the "warp-scan + shared-memory
+// transpose" of north_star (iii).  Lists longer than the staging buffer are written directly.
 // ------------------------------------------------------------------------------------------
-constexpr int M2I_THREADS = 256;
+constexpr int M2I_THREADS = 512;
 constexpr int M2I_WARPS = M2I_THREADS / 32;
+constexpr int STAGE_INTS = 16384;              // 64 KB staging buffer for one row's index list
+
+struct EmitScratch {
+    int seg_cnt[32][32];
+    int cursor[32][32];
+    int total;
+};
+
+// words[0..W) complete and visible to the whole CTA (caller synchronised).  All threads of the CTA call this.
+template <int NWARPS>
+__device__ __forceinline__ void emit_row(const uint32_t* words, int W, int n, int multiple_of, int32_t* __restrict__ out,
+                                         int32_t* __restrict__ count_out, EmitScratch& sc, int32_t* stage) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- per (slice, class) population
+    const int S = (W + NWARPS - 1) / NWARPS;
+    const int i0 = min(W, warp * S), i1 = min(W, i0 + S);
+    int cnt = 0;
+    for (int i = i0; i < i1; i++) cnt += (words[i] >> lane) & 1u;
+    sc.seg_cnt[warp][lane] = cnt;
+    __syncthreads();
+    // ---- cursors: class totals -> exclusive scan over classes (warp 0)
+    if (warp == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) tot += sc.seg_cnt[w][lane];
+        int incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int run = incl - tot;
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) {
+            sc.cursor[w][lane] = run;
+            run += sc.seg_cnt[w][lane];
+        }
+        if (lane == 31) sc.total = incl;
+    }
+    __syncthreads();
+    const int total = sc.total;
+    const int padded = ((total + multiple_of - 1) / multiple_of) * multiple_of;
+    const bool staged = stage != nullptr && padded <= STAGE_INTS;
+    int32_t* dest = staged ? stage : out;
+    // ---- emit set columns
+    int pos = sc.cursor[warp][lane];
+    for (int i = i0; i < i1; i++) {
+        if ((words[i] >> lane) & 1u) dest[pos++] = 32 * i + lane;
+    }
+    // ---- pad with the first unset columns (ascending), write the count
+    if (warp == 0) {
+        int need = padded - total;
+        int done = 0;
+        for (int base = 0; base < W && done < need; base += 32) {
+            int i = base + lane;
+            uint32_t inv = 0;
+            if (i < W) {
+                inv = ~words[i];
+                int rem = n - 32 * i;
+                if (rem < 32) inv &= (1u << rem) - 1u;
+            }
+            int pc = __popc(inv);
+            int incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int r = done + incl - pc;
+            while (inv && r < need) {
+                int c = __ffs(inv) - 1;
+                inv &= inv - 1;
+                dest[total + r] = 32 * i + c;
+                r++;
+            }
+            done += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) *count_out = padded;
+    }
+    if (staged) {
+        __syncthreads();
+        // a row of fewer unset columns than the padding asks for leaves a gap the reference leaves uninitialised too:
+        // only [0, min(padded, n)) is defined
+        const int nout = min(padded, n);
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            const int n4 = nout >> 2;
+            const int4* s4 = reinterpret_cast<const int4*>(stage);
+            int4* o4 = reinterpret_cast<int4*>(out);
+            for (int j = tid; j < n4; j += NWARPS * 32) o4[j] = s4[j];
+            for (int j = (n4 << 2) + tid; j < nout; j += NWARPS * 32) out[j] = stage[j];
+        } else {
+            for (int j = tid; j < nout; j += NWARPS * 32) out[j] = stage[j];
+        }
+    }
+}
 
 template <bool PACKED>
 __global__ void __launch_bounds__(M2I_THREADS)
 mask_to_indices_kernel(const uint8_t* __restrict__ src, int32_t* __restrict__ indices,
                        int32_t* __restrict__ counts, int n, int pad_n, int multiple_of,
-                       int64_t total_bytes) {
-    extern __shared__ uint32_t words[];          // [W]
-    __shared__ int seg_cnt[M2I_WARPS][32];
-    __shared__ int cursor[M2I_WARPS][32];
-    __shared__ int s_total;
+                       int64_t total_bytes, int use_stage) {
+    extern __shared__ __align__(16) uint32_t dyn_smem[];     // [STAGE_INTS if use_stage][W]
+    __shared__ EmitScratch sc;
+    int32_t* stage = use_stage ? reinterpret_cast<int32_t*>(dyn_smem) : nullptr;
+    uint32_t* words = dyn_smem + (use_stage ? STAGE_INTS : 0);
 
     const int64_t row = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int W = (n + 31) >> 5;
 
     // ---- stage 1: build the row's words
@@ -120,11 +218,16 @@ mask_to_indices_kernel(const uint8_t* __restrict__ src, int32_t* __restrict__ in
             const int64_t byte = off >> 3;
             const int sh = (int)(off & 7);
             uint64_t acc = 0;
+            if ((byte & 3) == 0 && byte + 8 <= total_bytes) {       // two aligned words instead of five byte loads
+                const uint32_t* p32 = reinterpret_cast<const uint32_t*>(src + byte);
+                acc = (uint64_t)__ldg(p32) | ((uint64_t)__ldg(p32 + 1) << 32);
+            } else {
 #pragma unroll
-            for (int b = 0; b < 5; b++) {
-                int64_t a = byte + b;
-                uint32_t v = (a < total_bytes) ? (uint32_t)__ldg(src + a) : 0u;
-                acc |= (uint64_t)v << (8 * b);
+                for (int b = 0; b < 5; b++) {
+                    int64_t a = byte + b;
+                    uint32_t v = (a < total_bytes) ? (uint32_t)__ldg(src + a) : 0u;
+                    acc |= (uint64_t)v << (8 * b);
+                }
             }
             uint32_t w = (uint32_t)(acc >> sh);
             int rem = n - 32 * i;
@@ -151,75 +254,285 @@ mask_to_indices_kernel(const uint8_t* __restrict__ src, int32_t* __restrict__ in
         }
     }
     __syncthreads();
+    emit_row<M2I_WARPS>(words, W, n, multiple_of, indices + row * (int64_t)pad_n, counts + row, sc, stage);
+}
 
-    // ---- stage 2: per (slice, class) population
-    const int S = (W + M2I_WARPS - 1) / M2I_WARPS;
-    const int i0 = min(W, warp * S), i1 = min(W, i0 + S);
-    int cnt = 0;
-    for (int i = i0; i < i1; i++) cnt += (words[i] >> lane) & 1u;
-    seg_cnt[warp][lane] = cnt;
-    __syncthreads();
+// ------------------------------------------------------------------------------------------
+// select_columns: the full step's column selection in ONE kernel.
+// Replaces `random_and_topk` + `bitpack` + `mask_to_indices` of the reference's SparseDiffAttn
+// (src/chipmunk/modules/attn.py:76-84,132-139: torch.randint + torch.topk over the [B,H,G,N] column sums +
+// scatter_ + static-mask algebra + bit packing + the index kernel; and :141-150, torch.topk, on the uncompressed path).
+// One CTA (1024 threads) per (b,h,g) row of the column sums cs[row, 0:n] (bf16):
+//   pass A/B  exact k-th largest by a two-level radix select on the order-preserving 16-bit key of the bf16 value
+//             (256-bin histograms, one private copy per lane so a warp never collides with itself; runs of equal
+//             bins are merged in registers, which matters because column sums share their exponent bits);
+//   pass C0   ties at the threshold are ranked by column so that EXACTLY k columns are kept (torch.topk's choice
+//             among equal values is unspecified; ours is "lowest column first");
+//   pass C    bit = top-k | hash(seed,row,col) < random_prob; the row's bit words are assembled in shared memory;
+//   then      words = (words & group_is_sparse[g]) | static_words[g]   (reference :80-82), the flat little-endian
+//             bit-packed mask is written (what bitpack() would store) and the index list + padded count are emitted
+//             exactly as mask_to_indices would emit them from that mask.
+// Every pass streams the row in warp-contiguous, lane-coalesced 16-byte loads; after pass A it comes from L2.
+// ------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_WARPS = 32;
 
-    // ---- stage 3: cursors.  class totals -> exclusive scan over classes (warp 0)
-    if (warp == 0) {
-        int tot = 0;
+__device__ __forceinline__ uint32_t bf16_key(uint32_t u) {       // order-preserving: larger float <=> larger key
+    return (u & 0x8000u) ? (~u & 0xffffu) : (u | 0x8000u);
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+struct SelParams {
+    const __nv_bfloat16* cs;
+    int64_t cs_row_stride;
+    int n, k;
+    uint32_t rand_thr16;          // keep if 16-bit hash < rand_thr16  (0: no random columns)
+    uint32_t seed;
+    const uint32_t* static_words; // [static_rows, static_stride] or null
+    int64_t static_stride;
+    int static_rows;
+    const uint8_t* group_is_sparse;   // [static_rows] or null
+    uint32_t* packed_words;       // flat bit-packed mask viewed as aligned 32-bit words, or null
+    int32_t* indices;             // or null
+    int32_t* counts;
+    int pad_n, multiple_of;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS, 1) select_columns_kernel(const SelParams P) {
+    extern __shared__ __align__(16) uint32_t dyn_smem[];     // [STAGE_INTS][W]
+    __shared__ uint32_t hist[256 * 32];
+    __shared__ uint32_t tot[256];
+    __shared__ EmitScratch sc;
+    __shared__ int s_bin, s_krem;
+    __shared__ int warp_ties[SEL_WARPS];
+
+    int32_t* stage = reinterpret_cast<int32_t*>(dyn_smem);
+    uint32_t* words = dyn_smem + STAGE_INTS;
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = P.n, W = (n + 31) >> 5;
+    const __nv_bfloat16* rowp = P.cs + row * P.cs_row_stride;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(rowp) & 15) == 0;
+    // warp w owns columns [w * CW, (w + 1) * CW), CW a multiple of 256: a warp step covers 256 columns, 8 per lane
+    const int CW = (((n + SEL_WARPS - 1) / SEL_WARPS) + 255) & ~255;
+    const int wbeg = warp * CW, wend = min(n, wbeg + CW);
+
+    auto load8 = [&](int col0, uint32_t (&key)[8]) -> uint32_t {      // returns the valid mask
+        if (vec_ok && col0 + 8 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + col0));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int w = 0; w < M2I_WARPS; w++) tot += seg_cnt[w][lane];
-        int incl = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+            for (int j = 0; j < 4; j++) { key[2 * j] = bf16_key(w4[j] & 0xffffu); key[2 * j + 1] = bf16_key(w4[j] >> 16); }
+            return 0xffu;
         }
-        int run = incl - tot;
+        uint32_t vm = 0;
 #pragma unroll
-        for (int w = 0; w < M2I_WARPS; w++) {
-            cursor[w][lane] = run;
-            run += seg_cnt[w][lane];
+        for (int j = 0; j < 8; j++) {
+            key[j] = 0;
+            if (col0 + j < n) { key[j] = bf16_key((uint32_t)__bfloat16_as_ushort(rowp[col0 + j])); vm |= 1u << j; }
         }
-        if (lane == 31) s_total = incl;
-    }
-    __syncthreads();
-
-    // ---- stage 4: emit set columns
-    int32_t* out = indices + row * (int64_t)pad_n;
-    int pos = cursor[warp][lane];
-    for (int i = i0; i < i1; i++) {
-        if ((words[i] >> lane) & 1u) out[pos++] = 32 * i + lane;
-    }
-
-    // ---- stage 5: pad with the first unset columns (ascending), write the count
-    const int total = s_total;
-    const int padded = ((total + multiple_of - 1) / multiple_of) * multiple_of;
-    if (warp == 0) {
-        int need = padded - total;
-        int done = 0;
-        for (int base = 0; base < W && done < need; base += 32) {
-            int i = base + lane;
-            uint32_t inv = 0;
-            if (i < W) {
-                inv = ~words[i];
-                int rem = n - 32 * i;
-                if (rem < 32) inv &= (1u << rem) - 1u;
-            }
-            int pc = __popc(inv);
-            int incl = pc;
+        return vm;
+    };
+    auto clear_hist = [&]() {
+        for (int i = tid; i < 256 * 32; i += SEL_THREADS) hist[i] = 0;
+    };
+    // bins -> totals, then the bin holding the `want`-th largest: s_bin, s_krem = how many to take from that bin
+    auto find_bin = [&](int want) {
+        __syncthreads();
+        for (int b = warp * 8; b < warp * 8 + 8; b++) {
+            uint32_t v = hist[b * 32 + lane];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) tot[b] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins 255 - 8 l ... 248 - 8 l (descending)
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) s += (int)tot[255 - 8 * lane - j];
+            int incl = s;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int t = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += t;
             }
-            int r = done + incl - pc;
-            while (inv && r < need) {
-                int c = __ffs(inv) - 1;
-                inv &= inv - 1;
-                out[total + r] = 32 * i + c;
-                r++;
+            const int excl = incl - s;
+            const int all = __shfl_sync(0xffffffffu, incl, 31);
+            if (want > all) {                       // fewer valid columns than asked for: take everything
+                if (lane == 0) { s_bin = -1; s_krem = 0; }
+            } else if (excl < want && want <= incl) {
+                int run = excl;
+                for (int j = 0; j < 8; j++) {
+                    const int b = 255 - 8 * lane - j;
+                    const int c = (int)tot[b];
+                    if (want <= run + c) { s_bin = b; s_krem = want - run; break; }
+                    run += c;
+                }
             }
-            done += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) counts[row] = padded;
+        __syncthreads();
+    };
+
+    // ------------------------------------------------------------------ threshold (k-th largest key) and tie quota
+    uint32_t T = 0x20000u;        // keep key > T, and `need` of the keys == T   (0x20000: keep none)
+    int need = 0;
+    if (P.k >= n) {
+        T = 0; need = 0x7fffffff;                 // keep every column (key 0 only occurs for -NaN; still kept by key >= T)
+    } else if (P.k > 0) {
+        clear_hist();
+        __syncthreads();
+        {   // pass A: high byte
+            uint32_t cur = 0xffffffffu, cnt = 0;
+            for (int col = wbeg + lane * 8; col < wend; col += 256) {
+                uint32_t key[8];
+                const uint32_t vm = load8(col, key);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!((vm >> j) & 1u)) continue;
+                    const uint32_t b = key[j] >> 8;
+                    if (b == cur) cnt++;
+                    else { if (cnt) atomicAdd(&hist[cur * 32 + lane], cnt); cur = b; cnt = 1; }
+                }
+            }
+            if (cnt) atomicAdd(&hist[cur * 32 + lane], cnt);
+        }
+        find_bin(P.k);
+        const int b1 = s_bin, k1 = s_krem;
+        __syncthreads();
+        if (b1 < 0) {
+            T = 0; need = 0x7fffffff;
+        } else {
+            clear_hist();
+            __syncthreads();
+            {   // pass B: low byte of the keys in bin b1
+                uint32_t cur = 0xffffffffu, cnt = 0;
+                for (int col = wbeg + lane * 8; col < wend; col += 256) {
+                    uint32_t key[8];
+                    const uint32_t vm = load8(col, key);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (!((vm >> j) & 1u) || (int)(key[j] >> 8) != b1) continue;
+                        const uint32_t b = key[j] & 0xffu;
+                        if (b == cur) cnt++;
+                        else { if (cnt) atomicAdd(&hist[cur * 32 + lane], cnt); cur = b; cnt = 1; }
+                    }
+                }
+                if (cnt) atomicAdd(&hist[cur * 32 + lane], cnt);
+            }
+            find_bin(k1);
+            T = ((uint32_t)b1 << 8) | (uint32_t)s_bin;
+            need = s_krem;                        // 1 <= need <= #(key == T)
+            __syncthreads();
+        }
     }
+
+    // ------------------------------------------------------------------ pass C0: ties per warp (column order)
+    int tie_base = 0;
+    const bool rank_ties = need > 0 && need != 0x7fffffff;
+    if (rank_ties) {
+        int e = 0;
+        for (int col = wbeg + lane * 8; col < wend; col += 256) {
+            uint32_t key[8];
+            const uint32_t vm = load8(col, key);
+#pragma unroll
+            for (int j = 0; j < 8; j++) e += (((vm >> j) & 1u) && key[j] == T) ? 1 : 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
+        if (lane == 0) warp_ties[warp] = e;
+        __syncthreads();
+        for (int w = 0; w < warp; w++) tie_base += warp_ties[w];
+    }
+
+    // ------------------------------------------------------------------ pass C: the row's bit words
+    for (int i = tid; i < W; i += SEL_THREADS) words[i] = 0;
+    __syncthreads();
+    {
+        const uint32_t rowseed = mix32(P.seed ^ mix32((uint32_t)row * 0x9E3779B1u + 0x7F4A7C15u));
+        uint8_t* wbytes = reinterpret_cast<uint8_t*>(words);
+        int running = tie_base;
+        for (int col0 = wbeg; col0 < wend; col0 += 256) {
+            const int col = col0 + lane * 8;
+            uint32_t key[8];
+            uint32_t vm = 0;
+            if (col < wend) vm = load8(col, key);
+            uint32_t gt = 0, eq = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (!((vm >> j) & 1u)) continue;
+                gt |= (key[j] > T ? 1u : 0u) << j;
+                eq |= (key[j] == T ? 1u : 0u) << j;
+            }
+            uint32_t keep = gt;
+            if (need == 0x7fffffff) keep |= eq;
+            else if (rank_ties && __any_sync(0xffffffffu, eq != 0)) {
+                const int e = __popc(eq);
+                int incl = e;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                int r = running + incl - e;
+                uint32_t m = eq;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (r < need) keep |= 1u << j;
+                    r++;
+                }
+                running += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (P.rand_thr16) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const uint32_t h = mix32(((uint32_t)(col + j) >> 1) * 0x9E3779B1u ^ rowseed);
+                    keep |= ((h & 0xffffu) < P.rand_thr16 ? 1u : 0u) << j;
+                    keep |= ((h >> 16) < P.rand_thr16 ? 1u : 0u) << (j + 1);
+                }
+                keep &= vm;
+            }
+            if (col < wend) wbytes[col >> 3] = (uint8_t)keep;
+        }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ static mask algebra (reference :80-82)
+    if (P.static_words != nullptr || P.group_is_sparse != nullptr) {
+        const int g = (int)(row % P.static_rows);
+        const bool sparse = P.group_is_sparse == nullptr || P.group_is_sparse[g] != 0;
+        const uint32_t* sw = P.static_words ? P.static_words + (int64_t)g * P.static_stride : nullptr;
+        for (int i = tid; i < W; i += SEL_THREADS) {
+            uint32_t w = sparse ? words[i] : 0u;
+            if (sw) w |= __ldg(sw + i);
+            const int rem = n - 32 * i;
+            if (rem < 32) w &= (1u << rem) - 1u;
+            words[i] = w;
+        }
+        __syncthreads();
+    }
+    // ------------------------------------------------------------------ the flat bit-packed mask
+    if (P.packed_words != nullptr) {
+        const int64_t bit0 = row * (int64_t)n;
+        const int64_t gw0 = bit0 >> 5, gw1 = (bit0 + n - 1) >> 5;
+        const int sh = (int)(bit0 & 31);
+        const bool last_shared = ((bit0 + n) & 31) != 0;
+        for (int64_t gw = gw0 + tid; gw <= gw1; gw += SEL_THREADS) {
+            const int j = (int)(gw - gw0);
+            const uint32_t lo = j < W ? words[j] : 0u;
+            const uint32_t prev = (j > 0 && j - 1 < W) ? words[j - 1] : 0u;
+            const uint32_t v = sh ? ((lo << sh) | (prev >> (32 - sh))) : lo;
+            // words shared with the neighbouring rows are OR-ed into the (zero-initialised) buffer
+            if ((gw == gw0 && sh != 0) || (gw == gw1 && last_shared)) { if (v) atomicOr(P.packed_words + gw, v); }
+            else P.packed_words[gw] = v;
+        }
+    }
+    // ------------------------------------------------------------------ indices + counts (mask_to_indices order)
+    if (P.indices != nullptr)
+        emit_row<SEL_WARPS>(words, W, n, P.multiple_of, P.indices + row * (int64_t)P.pad_n, P.counts + row, sc, stage);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -376,16 +689,55 @@ static int launch_m2i(const uint8_t* src, int32_t* indices, int32_t* counts, int
     if (rows == 0) return CM_OK;
     if (!src || !indices || !counts) return CM_EINVAL;
     if (rows > 2147483647ll) return CM_EINVAL;
-    size_t smem = (size_t)((n + 31) / 32) * 4;
-    if (smem > 200 * 1024) return CM_EUNSUPPORTED;
+    const size_t wbytes = (size_t)((n + 31) / 32) * 4;
+    if (wbytes > 160 * 1024) return CM_EUNSUPPORTED;
+    // the staging buffer costs occupancy: short rows (a few hundred indices) go straight to global memory
+    const int use_stage = n >= 2048 ? 1 : 0;
+    const size_t smem = wbytes + (use_stage ? (size_t)STAGE_INTS * 4 : 0);
     auto kern = mask_to_indices_kernel<PACKED>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static unsigned long long configured = 0;
+    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), 227 * 1024);
+    if (rc) return rc;
     int64_t total_bytes = PACKED ? (rows * (int64_t)n + 7) / 8 : rows * (int64_t)n;
     kern<<<(unsigned)rows, M2I_THREADS, smem, (cudaStream_t)stream>>>(src, indices, counts, n, pad_n,
-                                                                     multiple_of, total_bytes);
+                                                                     multiple_of, total_bytes, use_stage);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int cm_select_columns(const void* cs, int64_t cs_row_stride, int64_t rows, int n, int k, float random_prob,
+                                 uint64_t seed, const uint32_t* static_words, int64_t static_stride_words, int static_rows,
+                                 const uint8_t* group_is_sparse, uint8_t* packed_out, int32_t* indices, int32_t* counts,
+                                 int pad_n, int multiple_of, void* stream) {
+    if (rows < 0 || n <= 0 || k < 0 || !(random_prob >= 0.f && random_prob < 1.f)) return CM_EINVAL;
+    if (rows == 0) return CM_OK;
+    if (!cs || cs_row_stride < n || rows > 2147483647ll) return CM_EINVAL;
+    if (!packed_out && !indices) return CM_EINVAL;
+    if (indices && (!counts || pad_n < n || multiple_of <= 0)) return CM_EINVAL;
+    if ((static_words || group_is_sparse) && static_rows <= 0) return CM_EINVAL;
+    if (static_words && static_stride_words < (n + 31) / 32) return CM_EINVAL;
+    if (packed_out && (reinterpret_cast<uintptr_t>(packed_out) & 3)) return CM_EALIGN;
+    const size_t wbytes = (size_t)((n + 31) / 32) * 4;
+    if (wbytes > 112 * 1024) return CM_EUNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (packed_out && (n & 31)) {
+        // rows share boundary words: those are OR-ed in, so the buffer starts from zero
+        cudaError_t e = cudaMemsetAsync(packed_out, 0, (size_t)(((rows * (int64_t)n + 31) / 32) * 4), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    SelParams P{};
+    P.cs = (const __nv_bfloat16*)cs; P.cs_row_stride = cs_row_stride; P.n = n; P.k = k;
+    uint32_t thr = (uint32_t)(random_prob * 65536.f + 0.5f);
+    P.rand_thr16 = thr > 65535u ? 65535u : thr;
+    P.seed = (uint32_t)(seed ^ (seed >> 32));
+    P.static_words = static_words; P.static_stride = static_stride_words; P.static_rows = static_rows > 0 ? static_rows : 1;
+    P.group_is_sparse = group_is_sparse;
+    P.packed_words = reinterpret_cast<uint32_t*>(packed_out); P.indices = indices; P.counts = counts;
+    P.pad_n = pad_n; P.multiple_of = multiple_of;
+    static unsigned long long configured = 0;
+    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(select_columns_kernel), 190 * 1024);
+    if (rc) return rc;
+    const size_t smem = wbytes + (size_t)STAGE_INTS * 4;
+    select_columns_kernel<<<(unsigned)rows, SEL_THREADS, smem, s>>>(P);
     return (int)cudaGetLastError();
 }
 

@@ -5,6 +5,9 @@ same cache algebra: the cache holds dense(q,k,v) - sparse(q,k,v) of the last ful
 sparse step returns cache + sparse(q,k,v)).  Differences, all on the B200 side of the boundary:
   * sparse steps with compressed indices turn the stored bit mask into indices with ONE fused
     kernel (bitmask_to_indices) instead of bitunpack + mask_to_indices;
+  * full steps select their columns with ONE kernel (select_columns: exact top-k by radix select + 1 % random
+    columns + static mask -> packed bit mask AND index lists) instead of torch.randint + torch.topk + scatter_ +
+    mask algebra + bitpack + mask_to_indices;
   * no padding copies: the kernels take any sequence length and strided q/k/v;
   * the delta add-back is always fused into the attention epilogue (csp_attn with o_scale=+-1),
     also on the `pad_qkv_before_kernel` path.
@@ -23,6 +26,8 @@ from ..util import GLOBAL_CONFIG, AttnStorage, LayerCounter
 # shared by all layers, set by initialize_static_mask (video models only)
 singleton_static_mask = None
 singleton_video_query_groups = None
+singleton_static_words = None       # the static mask of one head, bit-packed per row ([G, ceil(N/32)] int32): select_columns' input
+singleton_group_flags = None        # [G] bool: query groups that get top-k + random columns on top of the static mask
 
 
 class SparseDiffAttn(nn.Module):
@@ -59,9 +64,12 @@ class SparseDiffAttn(nn.Module):
         mask = mask[None, None].expand(1, local_heads_num, -1, -1).contiguous()
         sparse_groups = (mask.sum(dim=-1, keepdim=True) + topk) < (n_vid + txt_len)
 
-        global singleton_static_mask, singleton_video_query_groups
+        global singleton_static_mask, singleton_video_query_groups, singleton_static_words, singleton_group_flags
         singleton_static_mask = mask
         singleton_video_query_groups = sparse_groups
+        # every head shares the same static rows: one bit-packed copy for the selection kernel
+        singleton_static_words = ops.pack_rows_to_words(mask[0, 0])
+        singleton_group_flags = sparse_groups[0, 0, :, 0].contiguous()
 
     def random_and_topk(self, cs: Tensor, topk: int) -> Tensor:
         """1 % random columns + top-k column sums (+ static mask) -> bool mask [B,H,G,N]
@@ -82,24 +90,39 @@ class SparseDiffAttn(nn.Module):
         return self.storage.get_indices(), self.storage.get_counts()
 
     def _select_indices(self, cs: Tensor, q: Tensor, k: Tensor, multiple_of: int, bm: int):
+        """Column selection of a full step (reference modules/attn.py:132-150), one kernel launch.
+        GLOBAL_CONFIG['attn']['torch_selection'] = True falls back to the reference's torch formulation
+        (random_and_topk + bitpack + mask_to_indices), kept for A/B checks."""
         cfg = GLOBAL_CONFIG["attn"]
         kseq = k.shape[-2]
         tk = int(multiple_of * round((cfg["top_keys"] * kseq) / multiple_of))
         if cfg["should_compress_indices"]:
-            if tk > 0:
-                mask = self.random_and_topk(cs, tk)
-            else:
-                mask = singleton_static_mask[..., : cs.shape[-2], : cs.shape[-1]]
-            packed, shape = ops.bitpack(mask)
+            if cfg.get("torch_selection", False):
+                if tk > 0:
+                    mask = self.random_and_topk(cs, tk)
+                else:
+                    mask = singleton_static_mask[..., : cs.shape[-2], : cs.shape[-1]]
+                packed, shape = ops.bitpack(mask)
+                self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
+                self.storage.set_indices(packed)
+                return ops.mask_to_indices(mask, multiple_of, bm)
+            # tk == 0: static mask only (the group flags are ignored, reference :135)
+            static = singleton_static_words
+            flags = singleton_group_flags if tk > 0 else None
+            packed, shape, inds, counts = ops.select_columns(
+                cs, tk, multiple_of, 0.01 if tk > 0 else 0.0, static, flags, None, bm)
             self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
             self.storage.set_indices(packed)
-            return ops.mask_to_indices(mask, multiple_of, bm)
+            return inds, counts
         groups = (q.shape[-2] + bm - 1) // bm
         cs = cs[..., : (kseq + bm - 1) // bm, :kseq]
-        top = torch.topk(cs, k=tk, dim=-1).indices.to(torch.int32)
-        inds = torch.empty((*top.shape[:-1], q.shape[-2]), device=q.device, dtype=torch.int32)
-        inds[..., :tk] = top
-        counts = torch.full((q.shape[0], q.shape[1], groups), tk, device=q.device, dtype=torch.int32)
+        if cfg.get("torch_selection", False):
+            top = torch.topk(cs, k=tk, dim=-1).indices.to(torch.int32)
+            inds = torch.empty((*top.shape[:-1], q.shape[-2]), device=q.device, dtype=torch.int32)
+            inds[..., :tk] = top
+            counts = torch.full((q.shape[0], q.shape[1], groups), tk, device=q.device, dtype=torch.int32)
+        else:
+            _, _, inds, counts = ops.select_columns(cs, tk, multiple_of, 0.0, None, None, 0, bm, want_packed=False)
         self.storage.set_indices(inds)
         self.storage.set_counts(counts)
         return inds, counts

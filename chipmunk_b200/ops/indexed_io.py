@@ -29,3 +29,15 @@ def mask_to_indices(mask, multiple_of: int, pad_to_multiple_of: int) -> List[tor
 def bitmask_to_indices(packed, mask_shape, multiple_of: int, pad_to_multiple_of: int) -> List[torch.Tensor]:
     """bitunpack + mask_to_indices in one pass over the packed bits (B200 addition)."""
     return _t.bitmask_to_indices(packed, mask_shape, multiple_of, pad_to_multiple_of)
+
+
+def select_columns(cs, k: int, multiple_of: int, random_prob: float = 0.0, static_words=None, group_is_sparse=None,
+                   seed=None, pad_to_multiple_of: int = 192, want_packed: bool = True, want_indices: bool = True):
+    """random_and_topk + bitpack + mask_to_indices of a full step in one kernel (B200 addition; reference
+    src/chipmunk/modules/attn.py:76-84,132-150).  Returns (packed, mask_shape, indices, counts)."""
+    return _t.select_columns(cs, k, multiple_of, random_prob, static_words, group_is_sparse, seed,
+                             pad_to_multiple_of, want_packed, want_indices)
+
+
+def pack_rows_to_words(mask2d):
+    return _t.pack_rows_to_words(mask2d)

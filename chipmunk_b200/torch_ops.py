@@ -304,6 +304,77 @@ def bitmask_to_indices(packed, mask_shape, multiple_of, pad_to_multiple_of=192) 
     return [indices, counts]
 
 
+def pack_rows_to_words(mask2d: torch.Tensor) -> torch.Tensor:
+    """bool [R, n] -> int32 words [R, ceil(n/32)], bit c%32 of word c/32 = column c (each row padded to whole words):
+    the layout select_columns takes its static mask in.  One-time preprocessing (initialize_static_mask)."""
+    require_cuda(mask2d)
+    _chk(mask2d.dim() == 2 and mask2d.dtype == torch.bool, "pack_rows_to_words: bool [R, n] expected")
+    R, n = mask2d.shape
+    W = (n + 31) // 32
+    padded = torch.zeros(R, W * 32, dtype=torch.bool, device=mask2d.device)
+    padded[:, :n] = mask2d
+    packed, _ = bitpack(padded)
+    return packed.view(torch.int32).view(R, W)
+
+
+def select_columns(cs, k: int, multiple_of: int, random_prob: float = 0.0, static_words=None, group_is_sparse=None,
+                   seed=None, pad_to_multiple_of: int = 192, want_packed: bool = True, want_indices: bool = True):
+    """Top-k (+ random, + static mask) column selection of one full step, in one kernel (cm_select_columns).
+    cs [B,H,G,n] bf16 (last-dim stride 1, rows equally strided).  Returns (packed uint8 | None, mask_shape,
+    indices [B,H,G,pad_n] | None, counts [B,H,G] | None).  `seed` defaults to a draw from torch's CUDA generator, so
+    torch.manual_seed() governs the random columns as it governs the reference's torch.randint."""
+    require_cuda(cs)
+    _chk(cs.dim() == 4 and cs.dtype == torch.bfloat16, "select_columns: cs must be bf16 [B,H,G,n]")
+    _chk(cs.stride(3) == 1, "select_columns: cs.stride(3) must be 1")
+    B, H, G, n = cs.shape
+    rows = B * H * G
+    rs = cs.stride(2)
+    _chk(rows <= 1 or (cs.stride(1) == G * rs and cs.stride(0) == H * G * rs) or cs.is_contiguous(),
+         "select_columns: cs rows must be equally strided")
+    _chk(0 <= k, "select_columns: k must be >= 0")
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item()) if random_prob > 0 else 0
+    packed = indices = counts = None
+    if want_packed:
+        nbits = rows * n
+        buf = torch.empty(4 * ((nbits + 31) // 32), dtype=torch.uint8, device=cs.device)
+        packed = buf[: (nbits + 7) // 8]
+    if want_indices:
+        pad_n = ((n + pad_to_multiple_of - 1) // pad_to_multiple_of) * pad_to_multiple_of
+        indices = torch.empty(B, H, G, pad_n, dtype=torch.int32, device=cs.device)
+        counts = torch.empty(B, H, G, dtype=torch.int32, device=cs.device)
+    else:
+        pad_n = n
+    srows = 0
+    sstride = 0
+    if static_words is not None:
+        require_cuda(static_words)
+        _chk(static_words.dtype == torch.int32 and static_words.dim() == 2 and static_words.is_contiguous(),
+             "select_columns: static_words must be contiguous int32 [G, ceil(n/32)]")
+        _chk(static_words.shape[1] >= (n + 31) // 32, "select_columns: static_words rows are too short")
+        srows, sstride = static_words.shape
+    if group_is_sparse is not None:
+        require_cuda(group_is_sparse)
+        group_is_sparse = group_is_sparse.reshape(-1)
+        _chk(group_is_sparse.dtype in (torch.bool, torch.uint8) and group_is_sparse.is_contiguous(),
+             "select_columns: group_is_sparse must be bool [G]")
+        _chk(srows in (0, group_is_sparse.numel()), "select_columns: static_words and group_is_sparse must have the same rows")
+        srows = group_is_sparse.numel()
+    if srows:
+        _chk(G % srows == 0 or srows >= G, "select_columns: static rows must cover the query groups")
+        if srows > G:      # the reference slices [..., :qg, :n]
+            srows = G
+    with torch.cuda.device(cs.device):
+        check(lib.cm_select_columns(_ptr(cs), rs, rows, n, int(k), float(random_prob), int(seed) & (2 ** 64 - 1),
+                                    _ptr(static_words) if static_words is not None else None, sstride, srows,
+                                    _ptr(group_is_sparse) if group_is_sparse is not None else None,
+                                    _ptr(packed) if packed is not None else None,
+                                    _ptr(indices) if indices is not None else None,
+                                    _ptr(counts) if counts is not None else None,
+                                    pad_n, int(multiple_of), stream_ptr(cs.device)), "select_columns")
+    return packed, torch.Size((B, H, G, n)), indices, counts
+
+
 def bitpack(mask):
     require_cuda(mask)
     _chk(mask.dtype == torch.bool, "mask must be bool type")

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 1
+#define CM_ABI_VERSION 2
 
 enum {
     CM_OK = 0,
@@ -146,6 +146,22 @@ int cm_mask_to_indices(const uint8_t* mask, int32_t* indices, int32_t* counts,
  * (src/chipmunk/modules/attn.py:173-176). */
 int cm_bitmask_to_indices(const uint8_t* packed, int32_t* indices, int32_t* counts,
                           int64_t rows, int n, int pad_n, int multiple_of, void* stream);
+
+/* Column selection of a full attention step in one kernel.  Replaces `random_and_topk` + `bitpack` +
+ * `mask_to_indices` (src/chipmunk/modules/attn.py:76-84,132-139) and the `torch.topk` of the uncompressed path
+ * (:141-150).  For every row r of cs [rows, cs_row_stride] bf16 (rows = B*H*G, the column sums of one query group):
+ *     keep[c]  = c among the k largest of cs[r, 0:n]  (exactly k: equal values at the threshold are taken lowest
+ *                column first; torch.topk leaves that choice unspecified)
+ *              | hash(seed, r, c) < random_prob                      (the reference draws torch.randint(0,100)==0)
+ *     keep     = (keep & group_is_sparse[g]) | static_words[g]       g = r % static_rows   (either may be NULL)
+ * static_words: [static_rows, static_stride_words] uint32, bit c%32 of word c/32 = column c (rows padded to words).
+ * Outputs (each optional, at least one): packed_out = the flat little-endian bit mask bitpack() would produce
+ * (4-byte aligned, room for ceil(rows*n/32) words; zero-initialised here when rows share words);
+ * indices [rows, pad_n] / counts [rows] exactly as cm_mask_to_indices would emit them from that mask. */
+int cm_select_columns(const void* cs, int64_t cs_row_stride, int64_t rows, int n, int k, float random_prob,
+                      uint64_t seed, const uint32_t* static_words, int64_t static_stride_words, int static_rows,
+                      const uint8_t* group_is_sparse, uint8_t* packed_out, int32_t* indices, int32_t* counts,
+                      int pad_n, int multiple_of, void* stream);
 
 /* Replaces chipmunk::topk_indices (csrc/indexed_io/topk_indices.cu:145-222, chipmunk.cpp:58).
  * act: [B*R, C] of `dtype`; indices int32 [B*R, C]; counts int32 [B*R].
