@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
 
@@ -62,44 +64,86 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+static int load_encoder() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn) return e != cudaSuccess ? (int)e : (int)cudaErrorSymbolNotFound;
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+
+// ---- a small cache of encoded tensor maps: the operands of a denoising step (weights, caches, q/k/v buffers of a
+// compiled block) come back with the same address / shape / strides step after step, and cuTensorMapEncodeTiled is a
+// driver call of several microseconds -- comparable to a short kernel.  Keyed by every argument of the encoding and the
+// current device; 64 entries, round-robin replacement; guarded by a mutex (ops may be called from several threads).
+struct TmapKey {
+    const void* base; uint64_t d[4]; uint64_t s[3]; uint32_t box[4]; int rank, swz, dev;
+    bool operator==(const TmapKey& o) const {
+        if (base != o.base || rank != o.rank || swz != o.swz || dev != o.dev) return false;
+        for (int i = 0; i < 4; i++) if (box[i] != o.box[i]) return false;
+        for (int i = 0; i < 4; i++) if (d[i] != o.d[i]) return false;
+        for (int i = 0; i < 3; i++) if (s[i] != o.s[i]) return false;
+        return true;
+    }
+};
+constexpr int TMAP_CACHE = 64;
+static TmapKey g_keys[TMAP_CACHE];
+static CUtensorMap g_maps[TMAP_CACHE];
+static int g_used = 0, g_next = 0;
+static std::mutex g_tmap_mutex;
+
+static int encode_cached(CUtensorMap* map, const TmapKey& key) {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    for (int i = 0; i < g_used; i++)
+        if (g_keys[i] == key) { *map = g_maps[i]; return 0; }
+    int rc = load_encoder();
+    if (rc) return rc;
+    cuuint64_t gdim[4]; cuuint64_t gstr[3]; cuuint32_t box[4] = {1, 1, 1, 1}; cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < key.rank; i++) gdim[i] = key.d[i];
+    for (int i = 0; i + 1 < key.rank; i++) gstr[i] = key.s[i];
+    for (int i = 0; i < key.rank; i++) box[i] = key.box[i];
+    const CUtensorMapSwizzle sw = key.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : key.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : key.swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)key.rank, const_cast<void*>(key.base), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    const int slot = g_used < TMAP_CACHE ? g_used++ : (g_next++ % TMAP_CACHE);
+    g_keys[slot] = key;
+    g_maps[slot] = *map;
+    return 0;
+}
+
+int cached_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                        uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+    TmapKey k{};
+    k.base = base; k.rank = 2; k.swz = swizzle_bytes; k.d[0] = cols; k.d[1] = rows; k.s[0] = pitch_bytes;
+    k.box[0] = box_cols; k.box[1] = box_rows; k.box[2] = 1; k.box[3] = 1;
+    cudaGetDevice(&k.dev);
+    return encode_cached(map, k);
+}
+
+int encode_tmap_4d_bf16_sw128(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                              const uint32_t box[4]) {
+    TmapKey k{};
+    k.base = base; k.rank = 4; k.swz = 128;
+    for (int i = 0; i < 4; i++) k.d[i] = dims[i];
+    for (int i = 0; i < 3; i++) k.s[i] = strides_bytes[i];
+    for (int i = 0; i < 4; i++) k.box[i] = box[i];
+    cudaGetDevice(&k.dev);
+    return encode_cached(map, k);
+}
+
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                         uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
-    if (!g_encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || !fn) return e != cudaSuccess ? (int)e : (int)cudaErrorSymbolNotFound;
-        g_encode = (EncodeTiledFn)fn;
-    }
-    cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {pitch_bytes};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    return cached_tmap_2d_bf16(map, base, rows, cols, pitch_bytes, box_cols, box_rows, swizzle_bytes);
 }
 
 int encode_tmap_2d_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                               uint64_t pitch_bytes, uint32_t box_rows) {
-    if (!g_encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || !fn) return e != cudaSuccess ? (int)e : (int)cudaErrorSymbolNotFound;
-        g_encode = (EncodeTiledFn)fn;
-    }
-    cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {pitch_bytes};
-    cuuint32_t box[2] = {64, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    return cached_tmap_2d_bf16(map, base, rows, cols, pitch_bytes, 64, box_rows, 128);
 }
 }  // namespace cm

@@ -690,13 +690,13 @@ static int launch_m2i(const uint8_t* src, int32_t* indices, int32_t* counts, int
     if (!src || !indices || !counts) return CM_EINVAL;
     if (rows > 2147483647ll) return CM_EINVAL;
     const size_t wbytes = (size_t)((n + 31) / 32) * 4;
-    if (wbytes > 160 * 1024) return CM_EUNSUPPORTED;
+    if (wbytes > 128 * 1024) return CM_EUNSUPPORTED;
     // the staging buffer costs occupancy: short rows (a few hundred indices) go straight to global memory
     const int use_stage = n >= 2048 ? 1 : 0;
     const size_t smem = wbytes + (use_stage ? (size_t)STAGE_INTS * 4 : 0);
     auto kern = mask_to_indices_kernel<PACKED>;
     static unsigned long long configured = 0;
-    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), 227 * 1024);
+    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), 200 * 1024);   // + 8 KB static
     if (rc) return rc;
     int64_t total_bytes = PACKED ? (rows * (int64_t)n + 7) / 8 : rows * (int64_t)n;
     kern<<<(unsigned)rows, M2I_THREADS, smem, (cudaStream_t)stream>>>(src, indices, counts, n, pad_n,
@@ -734,7 +734,7 @@ extern "C" int cm_select_columns(const void* cs, int64_t cs_row_stride, int64_t 
     P.packed_words = reinterpret_cast<uint32_t*>(packed_out); P.indices = indices; P.counts = counts;
     P.pad_n = pad_n; P.multiple_of = multiple_of;
     static unsigned long long configured = 0;
-    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(select_columns_kernel), 190 * 1024);
+    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(select_columns_kernel), 180 * 1024);   // + 42 KB static
     if (rc) return rc;
     const size_t smem = wbytes + (size_t)STAGE_INTS * 4;
     select_columns_kernel<<<(unsigned)rows, SEL_THREADS, smem, s>>>(P);

@@ -21,6 +21,16 @@ int encode_tmap_2d_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows,
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                         uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
+// 4-D bf16 tensor [d3][d2][d1][d0] with d0 contiguous (a [B,H,N,128] attention operand with arbitrary batch / head / row
+// strides): boxes of box[0..3] elements, SWIZZLE_128B (box[0] = 64).  `strides_bytes` = byte strides of d1, d2, d3
+// (multiples of 16).  Out-of-range coordinates read as zero / are not written.  Results are cached per argument set
+// (encoding costs microseconds on the host and the operands of a diffusion step recur), see c_api.cu.
+int encode_tmap_4d_bf16_sw128(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                              const uint32_t box[4]);
+// cached forms of the 2-D encoders (same arguments, same result)
+int cached_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                        uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+
 // One thread: load the tile whose top-left element is (row, col) into `dst` (1024-byte aligned),
 // completing `bytes` on `bar`.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
@@ -28,6 +38,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::1 "
         "[%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
         : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::1 "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src_smem)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");

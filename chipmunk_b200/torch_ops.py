@@ -127,28 +127,43 @@ def csp_128_attn(q, k, v, indices, indices_counts):
     return o
 
 
+LEGACY_DENSE = False     # development A/B switch: the round-1 two-pass kernels (contiguous inputs only)
+
+
 def _launch_dense(q, k, v, p):
     require_cuda(q, k, v)
     _chk(q.dim() == 4 and q.shape[3] == 128, "Head dimension must be 128")
     _chk(q.dtype == k.dtype == v.dtype == torch.bfloat16, "dense_attn: q, k, v must be bfloat16")
     _chk(k.shape == v.shape and k.shape[:2] == q.shape[:2], "dense_attn: K/V shapes must match Q's batch and heads")
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t.stride(3) == 1, f"dense_attn: {n}.stride(3) must be 1")
+        _chk(all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0,
+             f"dense_attn: {n} must be 16-byte aligned in every stride")
     B, H, Nq, _ = q.shape
     Nk = k.shape[2]
     G = (Nq + QG - 1) // QG
-    o = torch.empty_like(q)
+    o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
     l = torch.empty(B, H, Nq, 1, dtype=torch.float32, device=q.device)
     cs = None
+    cs_stride = (Nk + 7) // 8 * 8
     if p is not None:
         _chk(p.dtype == torch.float32 and p.numel() >= B * H * Nq, "dense_colsum_attn: p must be fp32 [B,H,N,1]")
         _chk(tuple(p.shape[:2]) == (B, H), "dense_colsum_attn: p batch/head must match q")
         p = p.reshape(B, H, -1)[:, :, :Nq].contiguous()
-        cs = torch.empty(B, H, G, Nk, dtype=torch.bfloat16, device=q.device)
+        cs = torch.empty(B, H, G, cs_stride, dtype=torch.bfloat16, device=q.device)
     with torch.cuda.device(q.device):
-        check(lib.cm_dense_attn(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(l),
-                                _ptr(cs) if cs is not None else None,
-                                _ptr(p) if p is not None else None,
-                                B, H, Nq, Nk, Nk, stream_ptr(q.device)), "dense_attn")
+        if LEGACY_DENSE:
+            qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+            check(lib.cm_dense_attn(_ptr(qc), _ptr(kc), _ptr(vc), _ptr(o), _ptr(l),
+                                    _ptr(cs) if cs is not None else None, _ptr(p) if p is not None else None,
+                                    B, H, Nq, Nk, cs_stride, stream_ptr(q.device)), "dense_attn")
+        else:
+            check(lib.cm_dense_attn_strided(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(l),
+                                            _ptr(cs) if cs is not None else None, _ptr(p) if p is not None else None,
+                                            B, H, Nq, Nk, strides3(q), strides3(k), strides3(v), strides3(o),
+                                            cs_stride, stream_ptr(q.device)), "dense_attn")
+    if cs is not None and cs_stride != Nk:
+        cs = cs[..., :Nk]
     return o, cs, l
 
 

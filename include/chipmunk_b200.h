@@ -100,6 +100,15 @@ int cm_csp_attn_add_bcast(const void* q, const void* k, const void* v, const voi
 int cm_dense_attn(const void* q, const void* k, const void* v, void* o, float* l,
                   void* cs, const float* p, int B, int H, int Nq, int Nk,
                   int64_t cs_row_stride, void* stream);
+/* The same operators for strided q/k/v/o views ({batch, head, row} element strides, multiples of 8; FLUX hands
+ * q, k, v as views of one fused projection buffer, examples/flux layers.py:298), computed in ONE pass: o, l and the
+ * column sums come out of a single walk over Q K^T, as in the reference's dense_colsum_attn.cu:205-341.
+ * cs (if not NULL) is zero-initialised here; cs_row_stride >= Nk and a multiple of 8. */
+int cm_dense_attn_strided(const void* q, const void* k, const void* v, void* o, float* l, void* cs, const float* p,
+                          int B, int H, int Nq, int Nk,
+                          const int64_t q_strides[3], const int64_t k_strides[3],
+                          const int64_t v_strides[3], const int64_t o_strides[3],
+                          int64_t cs_row_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Column-sparse MLP, first GEMM.
