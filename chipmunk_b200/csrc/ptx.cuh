@@ -159,6 +159,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
 __device__ __forceinline__ void red_add_bf16x8(void* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// scalar bf16 reduction at the L2: *dst = bf16(*dst + v)
+__device__ __forceinline__ void red_add_bf16(void* dst, float v) {
+    const unsigned short h = __bfloat16_as_ushort(__float2bfloat16(v));
+    asm volatile("red.global.add.noftz.bf16 [%0], %1;\n" ::"l"(dst), "h"(h) : "memory");
+}
 // 1-D bulk reduction shared -> global: dst[i] = bf16(dst[i] + src[i]) performed at the L2 (noftz bf16 add).
 __device__ __forceinline__ void bulk_reduce_add_bf16_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;\n" ::"l"(dst),
@@ -338,6 +343,9 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
         "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");

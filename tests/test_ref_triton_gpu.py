@@ -71,7 +71,7 @@ def _ulp_close(a, b, what, mag=None, max_ulps=2, frac_off=2e-2):
     scale = torch.maximum(a32.abs(), b32.abs())
     if mag is not None:
         scale = torch.maximum(scale, mag.float().to(scale.device))
-    tol = max_ulps * 2.0 ** -8 * scale.clamp_min(2.0 ** -6)
+    tol = max_ulps * 2.0 ** -7 * scale.clamp_min(2.0 ** -6)      # one bf16 ulp of x is in (2^-8 |x|, 2^-7 |x|]
     bad = (a32 - b32).abs() > tol
     assert not bool(bad.any()), f"{what}: {int(bad.sum())} elements differ by more than {max_ulps} bf16 ulps"
     off = float((a != b).float().mean())
