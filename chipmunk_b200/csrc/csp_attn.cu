@@ -528,36 +528,15 @@ extern "C" int cm_csp_attn_add(const void* q, const void* k, const void* v, cons
                          o_strides, idx_row_stride, o_scale, 0, stream);
 }
 
-namespace cm { namespace attn {
-int launch_colsum(const __nv_bfloat16* q, const __nv_bfloat16* k, const float* p, __nv_bfloat16* cs, int B, int H,
-                  int Nq, int Nk, int64_t cs_row_stride, cudaStream_t stream);
-} }
+// cm_dense_attn (contiguous [B,H,N,128] operands) is the strided one-pass kernel of dense_attn.cu with packed strides.
+extern "C" int cm_dense_attn_strided(const void* q, const void* k, const void* v, void* o, float* l, void* cs, const float* p,
+                                     int B, int H, int Nq, int Nk, const int64_t q_strides[3], const int64_t k_strides[3],
+                                     const int64_t v_strides[3], const int64_t o_strides[3], int64_t cs_row_stride,
+                                     void* stream);
 
 extern "C" int cm_dense_attn(const void* q, const void* k, const void* v, void* o, float* l, void* cs,
                              const float* p, int B, int H, int Nq, int Nk, int64_t cs_row_stride, void* stream) {
-    if (B < 0 || H < 0 || Nq < 0 || Nk <= 0) return CM_EINVAL;
-    if ((int64_t)B * H * Nq == 0) return CM_OK;
-    if (!q || !k || !v || !o) return CM_EINVAL;
-    if (cs && (!p || cs_row_stride < Nk)) return CM_EINVAL;
-    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return CM_EALIGN;
-    if (!is_sm100()) return CM_EARCH;
-    Params P{};
-    P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
-    P.o = (__nv_bfloat16*)o;
-    P.indices = nullptr; P.counts = nullptr; P.l = l;
-    P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + Geo<true>::QROWS - 1) / Geo<true>::QROWS;
     const int64_t qst[3] = {(int64_t)H * Nq * D, (int64_t)Nq * D, D};
     const int64_t kst[3] = {(int64_t)H * Nk * D, (int64_t)Nk * D, D};
-    for (int i = 0; i < 3; i++) { P.qs[i] = qst[i]; P.os[i] = qst[i]; P.ks[i] = kst[i]; P.vs[i] = kst[i]; }
-    P.idx_row_stride = Nk;
-    P.o_scale = 1.f;
-    P.accumulate = 0;
-    P.wide = (reinterpret_cast<uintptr_t>(o) & 31) == 0 ? 1 : 0;
-    P.cache = nullptr;
-    int64_t tiles = (int64_t)B * H * P.G;
-    if (tiles > 2147483647ll) return CM_EINVAL;
-    P.num_tiles = (int)tiles;
-    int rc = launch_attn<true>(P, (cudaStream_t)stream);
-    if (rc != 0 || !cs) return rc;
-    return launch_colsum(P.q, P.k, p, (__nv_bfloat16*)cs, B, H, Nq, Nk, cs_row_stride, (cudaStream_t)stream);
+    return cm_dense_attn_strided(q, k, v, o, l, cs, p, B, H, Nq, Nk, qst, kst, kst, qst, cs_row_stride, stream);
 }

@@ -3,36 +3,35 @@
 // wgmma kernels that compute o, l -- and cs -- in one flash-attention loop, dense_colsum_attn.cu:205-341).
 //
 // Work unit: one (b, h, 128 query rows) tile, walked over all keys 128 at a time.  All eight softmax warps work on
-// that one tile, two threads per query row (64 keys each).  P has its own (triple-buffered) TMEM columns, so the next
-// S = Q K^T is issued as soon as the softmax threads have READ the current one -- before they have computed anything --
-// and the P.V products trail behind: the tensor pipe never waits for a softmax step and a softmax step never waits
-// for the tensor pipe (the 192/256-row kernels of csp_attn.cu keep P inside S and are bound by each block's serial
-// softmax -> P.V -> S chain).  The two threads of a row share nothing per step: each reads the whole 128-wide S row
-// for the maximum (TMEM reads are cheap) and exponentiates its own half, so the two warps of an SM sub-partition
-// drift apart and one's MUFU phase overlaps the other's loads / maxima / conversions.
+// that one tile -- two threads per query row, 64 keys each -- and S is double-buffered in TMEM, so the tensor pipe
+// always has the next S ready when a softmax step ends (the 192/256-row kernels of csp_attn.cu keep two query
+// blocks in flight instead and are bound by each block's serial softmax -> P.V -> S chain).
 //
-//   warp 9       TMA producer: Q tile once per tile; K / V tiles (128 rows x 256 B, two 64-wide halves, 128B-swizzled)
+//   warp 13      TMA producer: Q tile once per tile; K / V tiles (128 rows x 256 B, two 64-wide halves, 128B-swizzled)
 //                through a 4-slot ring.  4-D tensor maps: any batch / head / row stride, rows past N read as zero.
-//   warp 8       MMA issuer (one elected thread), per step k:
-//                  CS(k-1) = P(k-1)^T F(k-1)   SS, M=128 keys, N=16, K=128 queries -> TMEM CS   (column sums, see below)
-//                  S(k+1)  = Q K(k+1)^T        SS, M=128 N=128 K=128  -> TMEM S        (after s_free(k))
-//                  O      += P(k-1) V(k-1)     TS (P from its TMEM buffer), V as MN-major smem   (after p_full(k-1))
-//   warps 0-7    softmax: thread (row r, half h): S row -> maximum (whole row) -> lazy rescale -> exp2 of keys
-//                [64h, 64h+64) -> bf16 P into TMEM buffer k%3 (and, for the column sums, into shared memory).
+//   warp 12      MMA issuer (one elected thread):
+//                  S(k)    = Q K(k)^T           SS, M=128 N=128 K=128  -> TMEM S buffer k&1
+//                  CS(k)^T = P(k)^T F(k)^T      SS, M=128 keys, N=16, K=128 queries -> TMEM CS   (column sums, see below)
+//                  O      += P(k) V(k)          TS (P read from TMEM, where it overwrote S), V as MN-major smem
+//   warps 0-7    softmax: thread (row r, half h) owns keys [64h, 64h+64) of the step and head dims [64h, 64h+64) of O;
+//                the pair shares its tile maximum through shared memory (64-thread named barrier), running maximum
+//                with lazy rescale, exp2, bf16 P written over S in TMEM (and, for the column sums, to shared memory).
 //                Epilogue (same threads): O / l -> bf16 -> 128B-swizzled staging tile -> TMA store; l to global.
+//   warps 8-11   column-sum drain, one warp per TMEM lane quadrant: CS^T (key on the lane, group on the column) ->
+//                bf16 -> 16-byte red.global.add into cs.
 //
 // Column sums.  cs[b,h,g,j] = sum_{i in 192-row group g} exp(s_ij / sqrt(d)) p_i   (dense_colsum_attn.cu:267-277).
 // With P_ij = exp2(s_ij c - m_i c) in hand (m_i = the row's running reference maximum), that is
 //     cs[g, j] = sum_i P_ij f_i ,   f_i = exp2(m_i c + log2 p_i)   over the rows i of the tile that lie in group g:
 // a [128 keys x 128 queries] x [128 queries x 16] product per step, i.e. the TENSOR PIPE does the cross-row reduction
 // at 1/8 of the cost of S (A = P^T: the P tile in shared memory read MN-major; B = F: row 0 / row 1 hold the f_i of the
-// tile's first / second group, rows 2-15 zero).  Key j of the step lands on TMEM lane j, so the softmax threads of
-// half 0 pick their key's two sums up at the next step and add them into cs with a bf16 reduction at the L2.
-// A 128-row tile overlaps at most two 192-row groups and every group is covered by two tiles: each cs element
-// receives exactly two partial sums (fp32-accumulated over up to 128 rows each, then bf16).  The reference reduces
-// twelve warps' bf16 partials with shared-memory atomics.
+// tile's first / second group, rows 2-15 zero).  (Round 2 first used an M=64 MMA of F x P: same result, but as
+// expensive as a full S and on the S -> softmax -> P.V chain.)  A 128-row tile overlaps at most two 192-row groups
+// and every group is covered by two tiles, so each cs element receives exactly two bf16 partial sums
+// (fp32-accumulated over up to 128 rows each), added at the L2.  The reference reduces twelve warps' bf16 partials
+// with shared-memory atomics.
 //
-// TMEM (512 columns): S [0,128)  P0/P1/P2 [128,320)  O [320,448)  CS [448,464).
+// TMEM (512 columns): S0 [0,128)  S1 [128,256)  O [256,384)  CS [384,400).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -53,10 +52,11 @@ constexpr int NSLOT = 4;
 constexpr int TILE_BYTES = 128 * 256;          // 32 KB: Q tile, K/V slot, P tile, output staging
 constexpr int HALF_BYTES = TILE_BYTES / 2;     // one 64-wide half: 128 rows x 128 B
 constexpr int F_BYTES = 4096;                  // B operand of the column-sum MMA: two 64-query halves x (16 rows x 128 B)
-constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + TILE_BYTES /*P / staging*/ + F_BYTES + NSLOT * TILE_BYTES + 1024 /*align*/;
-constexpr int NUM_THREADS = 384;               // warps 0-7 softmax | 8 MMA | 9 TMA | 10-11 idle
-constexpr int WARP_MMA = 8, WARP_TMA = 9;
-constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 320, TM_CS = 448;
+constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + TILE_BYTES /*P / staging*/ + NSLOT * TILE_BYTES + F_BYTES + 1024 /*align*/;
+constexpr int NUM_THREADS = 512;               // warps 0-7 softmax | 8-11 column-sum drain (one per TMEM lane quadrant) | 12 MMA | 13 TMA | 14-15 idle
+constexpr int WARP_DRAIN0 = 8, WARP_MMA = 12, WARP_TMA = 13;
+constexpr int REG_SOFTMAX = 192, REG_OTHER = 64;    // setmaxnreg budgets: 256 x 192 + 256 x 64 = 64 K registers
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_CS = 384;
 
 struct Params {
     float* l;                  // [B,H,Nq] or null
@@ -72,10 +72,8 @@ struct Params {
 struct __align__(8) Barriers {
     uint64_t q_full, q_empty;
     uint64_t kv_full[NSLOT], kv_empty[NSLOT];
-    uint64_t s_full, s_free;
-    uint64_t p_full[2];        // by step parity: the MMA thread may lag the softmax threads by more than one step
-    uint64_t pv_done[3];       // one per P buffer
-    uint64_t cs_full;
+    uint64_t s_full[2];
+    uint64_t p_full, pv_done, cs_full, cs_empty;
 };
 
 // coordinates (row, head, batch) placed at the positions the tensor map wants them
@@ -95,6 +93,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float s_mx[2][2 * BM];      // tile maxima of the two half-row threads, double-buffered by step parity
     __shared__ float s_lx[2 * BM];         // partial row sums, exchanged in the epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -104,10 +103,9 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     if (tid == 0) {
         mbar_init(&bar.q_full, 1); mbar_init(&bar.q_empty, 1);
         for (int i = 0; i < NSLOT; i++) { mbar_init(&bar.kv_full[i], 1); mbar_init(&bar.kv_empty[i], 1); }
-        mbar_init(&bar.s_full, 1); mbar_init(&bar.s_free, 256);
-        mbar_init(&bar.p_full[0], 256); mbar_init(&bar.p_full[1], 256);
-        for (int i = 0; i < 3; i++) mbar_init(&bar.pv_done[i], 1);
-        mbar_init(&bar.cs_full, 1);
+        mbar_init(&bar.s_full[0], 1); mbar_init(&bar.s_full[1], 1);
+        mbar_init(&bar.p_full, 256); mbar_init(&bar.pv_done, 1);
+        mbar_init(&bar.cs_full, 1); mbar_init(&bar.cs_empty, 4);
         fence_mbar_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
@@ -115,7 +113,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
     }
     if (HAS_CS) {
-        // rows 2-15 of F stay zero for the whole kernel
+        // rows 2-15 of the F operand stay zero for the whole kernel
         for (int i = tid; i < F_BYTES / 4; i += NUM_THREADS)
             asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(sF + 4 * i), "r"(0u) : "memory");
         fence_proxy_async_smem();
@@ -128,6 +126,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 
     if (warp == WARP_TMA) {
         // =================================================================================== TMA producer
+        setmaxnreg_dec<REG_OTHER>();
         if (lane == 0) {
             uint32_t job = 0, it = 0;
             auto load_kv = [&](const CUtensorMap* map, const int8_t* pos, int kstep, int h, int b) {
@@ -146,122 +145,154 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 const Coord cq = coords(P.pos[0], 0, t * BM, h, b);
                 tma_load_4d(sQ, &tm_q, &bar.q_full, 0, cq.c[1], cq.c[2], cq.c[3]);
                 tma_load_4d(sQ + HALF_BYTES, &tm_q, &bar.q_full, 64, cq.c[1], cq.c[2], cq.c[3]);
-                // consumption order of the ring: K0, then per step k: K(k+1), V(k-1); finally V(nk-1)
+                // consumption order of the ring: K0, K1, then V(k), K(k+2) for k = 0 ...
                 load_kv(&tm_k, P.pos[1], 0, h, b);
+                if (nk > 1) load_kv(&tm_k, P.pos[1], 1, h, b);
                 for (int k = 0; k < nk; k++) {
-                    if (k + 1 < nk) load_kv(&tm_k, P.pos[1], k + 1, h, b);
-                    if (k > 0) load_kv(&tm_v, P.pos[2], k - 1, h, b);
+                    load_kv(&tm_v, P.pos[2], k, h, b);
+                    if (k + 2 < nk) load_kv(&tm_k, P.pos[1], k + 2, h, b);
                 }
-                load_kv(&tm_v, P.pos[2], nk - 1, h, b);
             }
         }
     } else if (warp == WARP_MMA) {
         // =================================================================================== MMA issuer
-        uint32_t job = 0, it = 0, g = 0;       // ring jobs, tiles, global step index of the tile's first step
+        setmaxnreg_dec<REG_OTHER>();
+        uint32_t job = 0, it = 0, pc = 0, cc = 0;       // ring jobs, tiles, steps (p_full phases), cs phases
         const uint32_t idesc_s = umma_idesc_bf16(128, KT, 0, 0);
         const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
         const uint32_t idesc_cs = umma_idesc_bf16(128, 16, 1, 0);
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                 // K-major A: Q rows
         const uint64_t desc_k = umma_smem_desc(sKV, 16, 1024);                // K-major B: K rows
         const uint64_t desc_v = umma_smem_desc(sKV, HALF_BYTES, 1024);        // MN-major B: V rows (k = key, n = head dim)
-        const uint64_t desc_pt = umma_smem_desc(sP, HALF_BYTES, 1024);        // MN-major A: P rows (k = query, m = key)
         const uint64_t desc_f = umma_smem_desc(sF, 16, 1024);                 // K-major B: F rows (n = group row, k = query)
-        auto issue_S = [&](uint32_t slot) {
+        const uint64_t desc_p = umma_smem_desc(sP, HALF_BYTES, 1024);         // MN-major A: P rows (k = query, m = key)
+        auto issue_S = [&](uint32_t buf, uint32_t slot) {
             const uint64_t bd0 = desc_k + (uint64_t)(slot * (TILE_BYTES >> 4));
 #pragma unroll
             for (int k16 = 0; k16 < D / 16; k16++) {
                 const uint64_t off = (uint64_t)((((k16 >> 2) * HALF_BYTES) + (k16 & 3) * 32) >> 4);
-                umma_ss(tm + TM_S, desc_q + off, bd0 + off, idesc_s, k16 > 0);
+                umma_ss(tm + TM_S + buf * 128, desc_q + off, bd0 + off, idesc_s, k16 > 0);
             }
         };
-        auto issue_PV = [&](uint32_t pbuf, uint32_t slot, bool first) {
+        auto issue_PV = [&](uint32_t buf, uint32_t slot, bool first) {
             const uint64_t bd0 = desc_v + (uint64_t)(slot * (TILE_BYTES >> 4));
 #pragma unroll
             for (int j = 0; j < KT / 16; j++)
-                umma_ts(tm + TM_O, tm + TM_P + pbuf * 64 + j * 8, bd0 + (uint64_t)(j * (2048 >> 4)), idesc_pv, (!first) || j > 0);
+                umma_ts(tm + TM_O, tm + TM_S + buf * 128 + j * 8, bd0 + (uint64_t)(j * (2048 >> 4)), idesc_pv, (!first) || j > 0);
         };
-        auto issue_CS = [&]() {
+        auto issue_CS = [&]() {       // CS^T [128 keys x 16] = P^T [128 keys x 128 queries] . F^T [128 queries x 16]: 1/8 of an S
 #pragma unroll
-            for (int j = 0; j < BM / 16; j++) {       // 16 queries per MMA
+            for (int j = 0; j < BM / 16; j++) {
                 const uint64_t boff = (uint64_t)((((j >> 2) * (F_BYTES / 2)) + (j & 3) * 32) >> 4);
-                umma_ss(tm + TM_CS, desc_pt + (uint64_t)(j * (2048 >> 4)), desc_f + boff, idesc_cs, j > 0);
+                umma_ss(tm + TM_CS, desc_p + (uint64_t)(j * (2048 >> 4)), desc_f + boff, idesc_cs, j > 0);
             }
-        };
-        // step j (global index): softmax has written P(j) -> CS(j), P(j).V(j)
-        auto wait_p = [&](uint32_t j) { mbar_wait(&bar.p_full[j & 1], (j >> 1) & 1); };
-        auto do_pv = [&](uint32_t j, bool first) {
-            const uint32_t sv = job % NSLOT;
-            mbar_wait(&bar.kv_full[sv], (job / NSLOT) & 1);
-            job++;
-            tc_fence_after_sync();
-            if (elect_one()) {
-                issue_PV(j % 3, sv, first);
-                umma_commit(&bar.kv_empty[sv]);
-                umma_commit(&bar.pv_done[j % 3]);
-            }
-            __syncwarp();
-        };
-        auto do_cs = [&]() {
-            tc_fence_after_sync();
-            if (elect_one()) { issue_CS(); umma_commit(&bar.cs_full); }
-            __syncwarp();
         };
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
             mbar_wait(&bar.q_full, it & 1);
-            {   // S(0)
+            {   // prologue: S(0), S(1)
                 const uint32_t s0 = job % NSLOT;
                 mbar_wait(&bar.kv_full[s0], (job / NSLOT) & 1);
                 job++;
                 tc_fence_after_sync();
                 if (elect_one()) {
-                    issue_S(s0); umma_commit(&bar.s_full); umma_commit(&bar.kv_empty[s0]);
+                    issue_S(0, s0); umma_commit(&bar.s_full[0]); umma_commit(&bar.kv_empty[s0]);
                     if (nk == 1) umma_commit(&bar.q_empty);
                 }
                 __syncwarp();
-            }
-            for (int k = 0; k < nk; k++) {
-                if (k > 0) {
-                    wait_p(g + k - 1);
-#ifndef CM_CS_LATE
-                    if (HAS_CS) do_cs();
-#endif
-                }
-                if (k + 1 < nk) {
-                    mbar_wait(&bar.s_free, (g + k) & 1);            // every softmax thread has read S(k)
-                    const uint32_t sk = job % NSLOT;
-                    mbar_wait(&bar.kv_full[sk], (job / NSLOT) & 1);
+                if (nk > 1) {
+                    const uint32_t s1 = job % NSLOT;
+                    mbar_wait(&bar.kv_full[s1], (job / NSLOT) & 1);
                     job++;
                     tc_fence_after_sync();
                     if (elect_one()) {
-                        issue_S(sk); umma_commit(&bar.s_full); umma_commit(&bar.kv_empty[sk]);
-                        if (k + 2 == nk) umma_commit(&bar.q_empty);
+                        issue_S(1, s1); umma_commit(&bar.s_full[1]); umma_commit(&bar.kv_empty[s1]);
+                        if (nk == 2) umma_commit(&bar.q_empty);
                     }
                     __syncwarp();
                 }
-                if (k > 0) do_pv(g + k - 1, k == 1);
-#ifdef CM_CS_LATE
-                if (HAS_CS && k > 0) do_cs();
-#endif
             }
-            wait_p(g + nk - 1);
-            if (HAS_CS) do_cs();
-            do_pv(g + nk - 1, nk == 1);
-            g += nk;
+            for (int k = 0; k < nk; k++) {
+                const uint32_t sv = job % NSLOT;
+                mbar_wait(&bar.kv_full[sv], (job / NSLOT) & 1);
+                job++;
+                uint32_t sk = 0;
+                const bool more = k + 2 < nk;
+                if (more) {
+                    sk = job % NSLOT;
+                    mbar_wait(&bar.kv_full[sk], (job / NSLOT) & 1);
+                    job++;
+                }
+                if (HAS_CS && cc > 0) mbar_wait(&bar.cs_empty, (cc - 1) & 1);      // the previous column sums have left TMEM
+                mbar_wait(&bar.p_full, pc & 1); pc++;
+                tc_fence_after_sync();
+                if (elect_one()) {
+                    if (HAS_CS) { issue_CS(); umma_commit(&bar.cs_full); }
+                    issue_PV(k & 1, sv, k == 0);
+                    umma_commit(&bar.kv_empty[sv]);
+                    umma_commit(&bar.pv_done);
+                    if (more) {
+                        issue_S(k & 1, sk); umma_commit(&bar.s_full[k & 1]); umma_commit(&bar.kv_empty[sk]);
+                        if (k + 3 == nk) umma_commit(&bar.q_empty);
+                    }
+                }
+                __syncwarp();
+                if (HAS_CS) cc++;
+            }
+        }
+    } else if (warp >= WARP_DRAIN0 && warp < WARP_DRAIN0 + 4) {
+        // =================================================================================== column-sum drain
+        // CS^T sits in TMEM as [128 lanes = keys of the step] x [column 0 / 1 = the tile's first / second group]: warp q
+        // reads lane quadrant q, gathers 8 consecutive keys per lane group with shuffles and adds them into cs with
+        // 16-byte bf16 reductions at the L2 (each cs element receives two such partial sums, from two tiles)
+        setmaxnreg_dec<REG_OTHER>();
+        if (HAS_CS) {
+            const int q4 = warp - WARP_DRAIN0;
+            const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+            uint32_t cc = 0;
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+                const int t = tile % P.tiles_per_head, bh = tile / P.tiles_per_head;
+                const int row0 = t * BM;
+                const int gA = row0 / QG;
+                const bool has_b = row0 + BM - 1 >= QG * (gA + 1) && gA + 1 < P.G;
+                __nv_bfloat16* cs_a = P.cs + ((int64_t)bh * P.G + gA) * P.cs_stride;
+                __nv_bfloat16* cs_b = cs_a + P.cs_stride;
+                const int base = lane & ~7;
+                const bool for_b = (lane & 4) != 0;
+                for (int k = 0; k < nk; k++, cc++) {
+                    mbar_wait(&bar.cs_full, cc & 1);
+                    tc_fence_after_sync();
+                    uint32_t c0, c1;
+                    tmem_ld_32x32b_x2(tm + TM_CS + lane_off, c0, c1);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar.cs_empty);
+                    const uint32_t nb = __shfl_down_sync(0xffffffffu, c0, 1), nb1 = __shfl_down_sync(0xffffffffu, c1, 1);
+                    const uint32_t pa = pack_bf16x2(__uint_as_float(c0), __uint_as_float(nb));     // valid on even lanes
+                    const uint32_t pb = pack_bf16x2(__uint_as_float(c1), __uint_as_float(nb1));
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t va = __shfl_sync(0xffffffffu, pa, base + 2 * j);
+                        const uint32_t vb = __shfl_sync(0xffffffffu, pb, base + 2 * j);
+                        w[j] = for_b ? vb : va;
+                    }
+                    const int key = k * KT + q4 * 32 + base;             // first of this lane group's 8 keys
+                    if ((lane & 3) == 0 && key < P.cs_stride && (!for_b || has_b))
+                        red_add_bf16x8((for_b ? cs_b : cs_a) + key, w[0], w[1], w[2], w[3]);
+                }
+            }
         }
     } else if (warp < 8) {
         // =================================================================================== softmax + epilogue
+        setmaxnreg_inc<REG_SOFTMAX>();
         const int q4 = warp & 3, hf = warp >> 2;
         const int r_in_tile = q4 * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-        const uint32_t tS = tm + TM_S + lane_off;
         const uint32_t tO = tm + TM_O + lane_off + hf * 64;
         const uint32_t bar_id = 1 + q4;
-        // MUFU turn-taking between the two warps of an SM sub-partition (they share its 4-lane MUFU): warp (q4, 0) and
-        // warp (q4, 1) exponentiate alternately, so one's loads / maxima / conversions / stores run under the other's
-        // exp2 phase instead of both phases colliding (FA3-style ping-pong with 64-thread named barriers)
-        const uint32_t tok_mine = 7 + 2 * q4 + hf, tok_other = 7 + 2 * q4 + (hf ^ 1);
-        if (hf == 1) named_bar_arrive(tok_other, 64);        // half 0 goes first
-        uint32_t g = 0;                    // global step index (phases of s_full / s_free / p_full / pv_done / cs_full)
+        uint32_t sc0 = 0, sc1 = 0;         // uses of each S buffer
+        uint32_t gstep = 0;                // steps done by this CTA (phases of p_full / pv_done / cs_full)
         const uint32_t sw = (uint32_t)(r_in_tile & 7);
         const uint64_t c2 = pack_f32x2(SCALE_LOG2, SCALE_LOG2);
 
@@ -274,82 +305,43 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             named_bar_sync(5, 256);
             float lp = -INFINITY;          // log2 of the previous step's l of this row (column sums)
             uint32_t f_addr = 0, f_other = 0;
-            // column sums: this thread drains key (32 q4 + lane) of every step into the tile's first / second group
-            const int gA = (t * BM) / QG;
-            const bool has_b = t * BM + BM - 1 >= QG * (gA + 1) && gA + 1 < P.G;
-            __nv_bfloat16* cs_a = nullptr;
-            __nv_bfloat16* cs_b = nullptr;
             if (HAS_CS && hf == 0) {
                 const float pv = row_ok ? __ldg(P.p + (int64_t)bh * P.Nq + row) : 0.f;
                 lp = pv > 0.f ? __log2f(pv) : -INFINITY;
+                const int gA = (t * BM) / QG;
                 const uint32_t r01 = row >= QG * (gA + 1) ? 1u : 0u;      // F row of this query's group
                 const uint32_t base = sF + (uint32_t)(r_in_tile >> 6) * (F_BYTES / 2) + (uint32_t)(r_in_tile & 7) * 2;
                 const uint32_t chunk = (uint32_t)((r_in_tile & 63) >> 3);
                 f_addr = base + r01 * 128 + ((chunk ^ r01) << 4);
                 f_other = base + (r01 ^ 1u) * 128 + ((chunk ^ (r01 ^ 1u)) << 4);
-                cs_a = P.cs + ((int64_t)bh * P.G + gA) * P.cs_stride + r_in_tile;      // (drain_cs rebases to the 8-key chunk)
-                cs_b = cs_a + P.cs_stride;
             }
-            auto drain_cs = [&](int kstep) {       // column sums of step `kstep` (cs_full already waited): TMEM lane = key
-                uint32_t c0, c1;
-                tmem_ld_32x32b_x2(tm + TM_CS + lane_off, c0, c1);
-                tmem_ld_wait();
-                // lanes 8j .. 8j+7 hold 8 consecutive keys: gather them into lane 8j (group A) / lane 8j+4 (group B) as four
-                // bf16 pairs, so that the sums leave as 16-byte reductions (a scalar bf16 red per key is 8x the L2 atomics)
-                const uint32_t nb = __shfl_down_sync(0xffffffffu, c0, 1), nb1 = __shfl_down_sync(0xffffffffu, c1, 1);
-                const uint32_t pa = pack_bf16x2(__uint_as_float(c0), __uint_as_float(nb));     // valid on even lanes
-                const uint32_t pb = pack_bf16x2(__uint_as_float(c1), __uint_as_float(nb1));
-                const int base = lane & ~7;
-                const bool for_b = (lane & 4) != 0;
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t va = __shfl_sync(0xffffffffu, pa, base + 2 * j);
-                    const uint32_t vb = __shfl_sync(0xffffffffu, pb, base + 2 * j);
-                    w[j] = for_b ? vb : va;
-                }
-                const int key = kstep * KT + q4 * 32 + base;         // first of the 8 keys
-                if ((lane & 3) == 0 && key < P.cs_stride) {
-                    __nv_bfloat16* dst = (for_b ? cs_b : cs_a) - r_in_tile + key;
-                    if (!for_b || has_b) red_add_bf16x8(dst, w[0], w[1], w[2], w[3]);
-                }
-            };
             float m_ref = -INFINITY, l_sum = 0.f;
 
-            for (int k = 0; k < nk; k++, g++) {
+            for (int k = 0; k < nk; k++, gstep++) {
+                const uint32_t buf = k & 1;
+                const uint32_t tS = tm + TM_S + buf * 128 + lane_off;
                 const int valid = P.Nk - k * KT;                 // >= 128 except on the last step
-                mbar_wait(&bar.s_full, g & 1);
+                if (buf == 0) { mbar_wait(&bar.s_full[0], sc0 & 1); sc0++; } else { mbar_wait(&bar.s_full[1], sc1 & 1); sc1++; }
                 tc_fence_after_sync();
                 uint32_t s[64];
-                float m_tile;
-                {
-                    uint32_t o[64];                              // the partner's half: only its maximum is needed
-                    tmem_ld32(tS + (hf ^ 1) * 64, o);
-                    tmem_ld32(tS + (hf ^ 1) * 64 + 32, o + 32);
-                    tmem_ld32(tS + hf * 64, s);
-                    tmem_ld32(tS + hf * 64 + 32, s + 32);
-                    tmem_ld_wait();
-                    tc_fence_before_sync();
-                    mbar_arrive(&bar.s_free);                    // S may be overwritten by the next Q K^T
-                    if (valid < KT) {
+                tmem_ld32(tS + hf * 64, s);
+                tmem_ld32(tS + hf * 64 + 32, s + 32);
+                tmem_ld_wait();
+                if (valid < KT) {
 #pragma unroll
-                        for (int j = 0; j < 64; j++) {
-                            s[j] = (hf * 64 + j < valid) ? s[j] : 0xff800000u;
-                            o[j] = ((hf ^ 1) * 64 + j < valid) ? o[j] : 0xff800000u;
-                        }
-                    }
-                    float mx[4] = {__uint_as_float(s[0]), __uint_as_float(s[32]), __uint_as_float(o[0]), __uint_as_float(o[32])};
-#pragma unroll
-                    for (int j = 1; j < 31; j += 2) {
-                        mx[0] = fmax3(mx[0], __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
-                        mx[1] = fmax3(mx[1], __uint_as_float(s[32 + j]), __uint_as_float(s[32 + j + 1]));
-                        mx[2] = fmax3(mx[2], __uint_as_float(o[j]), __uint_as_float(o[j + 1]));
-                        mx[3] = fmax3(mx[3], __uint_as_float(o[32 + j]), __uint_as_float(o[32 + j + 1]));
-                    }
-                    m_tile = fmaxf(fmaxf(fmax3(mx[0], mx[1], __uint_as_float(s[31])), __uint_as_float(s[63])),
-                                   fmaxf(fmax3(mx[2], mx[3], __uint_as_float(o[31])), __uint_as_float(o[63])));
+                    for (int j = 0; j < 64; j++) s[j] = (hf * 64 + j < valid) ? s[j] : 0xff800000u;
                 }
-                // both threads of the row see the same S row and take the same decision
+                float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[32]);
+#pragma unroll
+                for (int j = 1; j < 31; j += 2) {
+                    mx0 = fmax3(mx0, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(s[32 + j]), __uint_as_float(s[32 + j + 1]));
+                }
+                const float m_part = fmaxf(fmaxf(mx0, __uint_as_float(s[31])), fmaxf(mx1, __uint_as_float(s[63])));
+                s_mx[buf][r_in_tile * 2 + hf] = m_part;
+                named_bar_sync(bar_id, 64);          // also: both threads have loaded their S half before either writes P over it
+                const float m_tile = fmaxf(m_part, s_mx[buf][r_in_tile * 2 + (hf ^ 1)]);
+                // (m_tile - m_ref) is NaN when both are -inf (a fully masked half cannot happen: valid >= 1): m_ref = -inf only on step 0
                 const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
                 if (__any_sync(0xffffffffu, need)) {
                     float alpha = 1.f;
@@ -359,7 +351,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                         l_sum *= alpha;
                     }
                     if (k > 0) {
-                        mbar_wait(&bar.pv_done[(g - 1) % 3], ((g - 1) / 3) & 1);     // O += P(k-1) V(k-1) has landed
+                        mbar_wait(&bar.pv_done, (gstep - 1) & 1);        // O += P(k-1) V(k-1) has landed
                         tc_fence_after_sync();
 #pragma unroll 1
                         for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -372,16 +364,22 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                         }
                     }
                 }
-                // P buffer g % 3 was last read by P(g-3).V(g-3)
-                if (g >= 3) mbar_wait(&bar.pv_done[g % 3], ((g - 3) / 3) & 1);
-                const uint32_t tP = tm + TM_P + (g % 3) * 64 + lane_off + hf * 32;
                 const float neg_m = -m_ref * SCALE_LOG2;
                 const uint64_t nm2 = pack_f32x2(neg_m, neg_m);
+                if (HAS_CS) {
+                    // the previous step's column-sum MMA has finished reading the P tile and F
+                    if (k > 0) mbar_wait(&bar.cs_full, (gstep - 1) & 1);
+                    if (hf == 0) {
+                        const float f = fast_exp2(m_ref * SCALE_LOG2 + lp);
+                        const uint32_t fb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(f));
+                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(f_addr), "h"((unsigned short)fb) : "memory");
+                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(f_other), "h"((unsigned short)0) : "memory");
+                    }
+                }
                 uint64_t acc[2] = {0ull, 0ull};
-                uint32_t pk[32];
-                named_bar_sync(tok_mine, 64);                        // my turn on the MUFU
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const uint64_t x = ffma2(pack_f32x2(__uint_as_float(s[c0 + j]), __uint_as_float(s[c0 + j + 1])), c2, nm2);
@@ -389,37 +387,24 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                         unpack_f32x2(x, x0, x1);
                         const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
                         acc[(j >> 1) & 1] = fadd2(acc[(j >> 1) & 1], pack_f32x2(p0, p1));
-                        pk[(c0 + j) >> 1] = pack_bf16x2(p0, p1);
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st_32x32b_x16(tP + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(pk + (c0 >> 1)));
+                    tmem_st_32x32b_x16(tS + hf * 32 + (c0 >> 1), pk);
+                    if (HAS_CS) {
+                        const uint32_t prow = sP + hf * HALF_BYTES + r_in_tile * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            st_shared_v4(prow + ((((uint32_t)(c0 >> 3) + q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    }
                 }
-                named_bar_arrive(tok_other, 64);                     // the partner warp's turn
                 float a0, a1, a2, a3;
                 unpack_f32x2(acc[0], a0, a1);
                 unpack_f32x2(acc[1], a2, a3);
                 l_sum += (a0 + a1) + (a2 + a3);
-                if (HAS_CS) {
-                    if (k > 0) {
-                        // the previous step's column-sum MMA is done: its sums can be collected, and the P tile / F rewritten
-                        mbar_wait(&bar.cs_full, (g - 1) & 1);
-                        tc_fence_after_sync();
-                        if (hf == 0) drain_cs(k - 1);
-                    }
-                    const uint32_t prow = sP + hf * HALF_BYTES + r_in_tile * 128;
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        st_shared_v4(prow + (((uint32_t)q ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    if (hf == 0) {
-                        const float f = fast_exp2(m_ref * SCALE_LOG2 + lp);
-                        const unsigned short fb = __bfloat16_as_ushort(__float2bfloat16(f));
-                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(f_addr), "h"(fb) : "memory");
-                        asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(f_other), "h"((unsigned short)0) : "memory");
-                    }
-                    fence_proxy_async_smem();
-                }
                 tmem_st_wait();
+                if (HAS_CS) fence_proxy_async_smem();
                 tc_fence_before_sync();
-                mbar_arrive(&bar.p_full[g & 1]);
+                mbar_arrive(&bar.p_full);
             }
             // ---- epilogue: O / l -> bf16 -> staging tile -> TMA store
             s_lx[r_in_tile * 2 + hf] = l_sum;
@@ -427,12 +412,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             const float l_tot = l_sum + s_lx[r_in_tile * 2 + (hf ^ 1)];
             const float inv = 1.f / l_tot;
             if (hf == 0 && row_ok && P.l) P.l[(int64_t)bh * P.Nq + row] = 1.f / (fast_exp2(m_ref * SCALE_LOG2) * l_tot);
-            if (HAS_CS) {
-                mbar_wait(&bar.cs_full, (g - 1) & 1);            // the last column sums; the P tile is free for the staging
-                tc_fence_after_sync();
-                if (hf == 0) drain_cs(nk - 1);
-            }
-            mbar_wait(&bar.pv_done[(g - 1) % 3], ((g - 1) / 3) & 1);
+            mbar_wait(&bar.pv_done, (gstep - 1) & 1);
             tc_fence_after_sync();
             {
                 uint32_t r[64];
@@ -460,6 +440,8 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             }
         }
         if (tid == 0) bulk_wait<0>();
+    } else {
+        setmaxnreg_dec<REG_OTHER>();        // warps 14-15: idle (setmaxnreg is warpgroup-wide)
     }
 
     tc_fence_before_sync();

@@ -127,9 +127,6 @@ def csp_128_attn(q, k, v, indices, indices_counts):
     return o
 
 
-LEGACY_DENSE = False     # development A/B switch: the round-1 two-pass kernels (contiguous inputs only)
-
-
 def _launch_dense(q, k, v, p):
     require_cuda(q, k, v)
     _chk(q.dim() == 4 and q.shape[3] == 128, "Head dimension must be 128")
@@ -152,16 +149,10 @@ def _launch_dense(q, k, v, p):
         p = p.reshape(B, H, -1)[:, :, :Nq].contiguous()
         cs = torch.empty(B, H, G, cs_stride, dtype=torch.bfloat16, device=q.device)
     with torch.cuda.device(q.device):
-        if LEGACY_DENSE:
-            qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
-            check(lib.cm_dense_attn(_ptr(qc), _ptr(kc), _ptr(vc), _ptr(o), _ptr(l),
-                                    _ptr(cs) if cs is not None else None, _ptr(p) if p is not None else None,
-                                    B, H, Nq, Nk, cs_stride, stream_ptr(q.device)), "dense_attn")
-        else:
-            check(lib.cm_dense_attn_strided(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(l),
-                                            _ptr(cs) if cs is not None else None, _ptr(p) if p is not None else None,
-                                            B, H, Nq, Nk, strides3(q), strides3(k), strides3(v), strides3(o),
-                                            cs_stride, stream_ptr(q.device)), "dense_attn")
+        check(lib.cm_dense_attn_strided(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(l),
+                                        _ptr(cs) if cs is not None else None, _ptr(p) if p is not None else None,
+                                        B, H, Nq, Nk, strides3(q), strides3(k), strides3(v), strides3(o),
+                                        cs_stride, stream_ptr(q.device)), "dense_attn")
     if cs is not None and cs_stride != Nk:
         cs = cs[..., :Nk]
     return o, cs, l

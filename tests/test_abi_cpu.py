@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(cm):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/chipmunk_b200.h but not exported"
     assert set(syms) == set(cm._lib.EXPORTS)
-    assert lib.cm_abi_version() == 1
+    assert lib.cm_abi_version() == 2      # round 2: + cm_select_columns, cm_dense_attn_strided
     lib.cm_strerror.restype = ctypes.c_char_p
     assert b"16-byte" in lib.cm_strerror(-2)
 

@@ -49,7 +49,9 @@ def test_sparse_diff_attn_steps(cm, oracle, cuda, compressed, pad):
         inds, counts = attn.storage.get_indices(), attn.storage.get_counts()
     o3 = attn(q2, k, v)
     ref = oracle.csp_attn(q2.cpu(), k.cpu(), v.cpu(), cache_before.cpu(), inds.cpu(), counts.cpu(), 1)
-    assert _rel(o3.cpu(), ref) < 4e-3
+    # two bf16 roundings (delta, then cache + delta) on both sides; the selection kernel emits the stored columns in
+    # mask_to_indices order, which changes the fp32 summation order of a few rows by one bf16 ulp
+    assert _rel(o3.cpu(), ref) < 5e-3
     assert torch.equal(attn.storage.get_out_cache(), cache_before), "a sparse step must not modify the cache"
     cache = attn.storage.get_out_cache()
     assert cache.shape == q.shape and cache.dtype == BF

@@ -93,13 +93,9 @@ def main():
             n = 5 if N < 100000 else 2
             t_new = timeit(lambda: T._launch_dense(q, k, v, None), n)
             t_cs = timeit(lambda: T._launch_dense(q, k, v, p), n)
-            T.LEGACY_DENSE = True
-            t_old = timeit(lambda: T._launch_dense(q, k, v, None), n)
-            t_old_cs = timeit(lambda: T._launch_dense(q, k, v, p), n)
-            T.LEGACY_DENSE = False
             t_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), n)
             print(f"H={H} N={N}: one-pass dense {t_new:.3f} ms ({fl / t_new / 1e9:.0f} TF/s), dense+colsum {t_cs:.3f} ms "
-                  f"({fl / t_cs / 1e9:.0f} TF/s-equiv) | round-1 dense {t_old:.3f} ms, dense+colsum (two passes) {t_old_cs:.3f} ms | "
+                  f"({fl / t_cs / 1e9:.0f} TF/s-equiv) | "
                   f"cuDNN SDPA {t_sdpa:.3f} ms ({fl / t_sdpa / 1e9:.0f} TF/s)", flush=True)
 
 
