@@ -43,6 +43,7 @@ def _load() -> C.CDLL:
         "cm_select_columns": ([vp, i64, i64, i32, i32, f32, C.c_uint64, vp, i64, i32, vp, vp, vp, vp, i32, i32, vp], i32),
         "cm_topk_indices": ([vp, i32, vp, vp, i32, i32, i32, f32, i32, f32, vp], i32),
         "cm_copy_indices": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, vp], i32),
+        "cm_gather_rows": ([vp, vp, vp, i64, i64, i64, i64, vp], i32),
         "cm_bitpack": ([vp, vp, i64, vp], i32),
         "cm_bitunpack": ([vp, vp, i64, vp], i32),
     }
@@ -56,7 +57,7 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTS = ("cm_abi_version", "cm_sm_count", "cm_strerror", "cm_csp_attn", "cm_csp_attn_add", "cm_csp_attn_add_bcast", "cm_dense_attn", "cm_dense_attn_strided",
            "cm_csp_mlp_mm1", "cm_csp_mlp_mm2", "cm_csp_scatter_add", "cm_mask_to_indices",
-           "cm_bitmask_to_indices", "cm_select_columns", "cm_topk_indices", "cm_copy_indices", "cm_bitpack",
+           "cm_bitmask_to_indices", "cm_select_columns", "cm_topk_indices", "cm_copy_indices", "cm_gather_rows", "cm_bitpack",
            "cm_bitunpack")
 
 

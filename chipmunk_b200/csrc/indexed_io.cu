@@ -845,3 +845,50 @@ extern "C" int cm_copy_indices(const void* src, void* dst, int elem_size, const 
         return CM_EUNSUPPORTED;
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------
+// Token reordering: dst[o, i, :] = src[o, perm[i], :].
+// The reference's 2-level patchify / 3-D voxel chunking (src/chipmunk/ops/patch.py:7-80, ops/voxel.py:9-99) are fixed
+// permutations of the token axis built from chains of einops rearranges (each a full copy); here the permutation is
+// cached on the host side and ONE gather moves the data: rows of `row_bytes` bytes, 16 bytes per thread when the rows
+// allow it (a [.., 128] bf16 token row is 16 such chunks: coalesced 256-byte reads and writes), else 2/4-byte elements.
+// HBM-bound: bytes = 2 x tensor size + 4 n.
+// ------------------------------------------------------------------------------------------
+namespace cm {
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ src, V* __restrict__ dst,
+                                                          const int32_t* __restrict__ perm, int64_t n_src, int64_t n_dst,
+                                                          int chunks_per_row, int64_t total_chunks) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total_chunks; c += stride) {
+        const int64_t r = c / chunks_per_row;
+        const int ch = (int)(c - r * chunks_per_row);
+        const int64_t o = r / n_dst, i = r - o * n_dst;
+        const int64_t j = __ldg(perm + i);
+        dst[c] = __ldg(src + (o * n_src + j) * chunks_per_row + ch);
+    }
+}
+}  // namespace cm
+
+extern "C" int cm_gather_rows(const void* src, void* dst, const int32_t* perm, int64_t outer, int64_t n_src, int64_t n_dst,
+                              int64_t row_bytes, void* stream) {
+    if (outer < 0 || n_src <= 0 || n_dst < 0 || row_bytes <= 0) return CM_EINVAL;
+    if (outer == 0 || n_dst == 0) return CM_OK;
+    if (!src || !dst || !perm) return CM_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes;
+    const int unit = (al & 15) == 0 ? 16 : (al & 7) == 0 ? 8 : (al & 3) == 0 ? 4 : (al & 1) == 0 ? 2 : 1;
+    const int64_t cpr = row_bytes / unit;
+    if (cpr > 2147483647ll) return CM_EINVAL;
+    const int64_t total = outer * n_dst * cpr;
+    int64_t want = (total + 255) / 256;
+    const int blocks = (int)(want < 1 ? 1 : (want > 148 * 32 ? 148 * 32 : want));
+    switch (unit) {
+        case 16: cm::gather_rows_kernel<uint4><<<blocks, 256, 0, s>>>((const uint4*)src, (uint4*)dst, perm, n_src, n_dst, (int)cpr, total); break;
+        case 8: cm::gather_rows_kernel<uint2><<<blocks, 256, 0, s>>>((const uint2*)src, (uint2*)dst, perm, n_src, n_dst, (int)cpr, total); break;
+        case 4: cm::gather_rows_kernel<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)src, (uint32_t*)dst, perm, n_src, n_dst, (int)cpr, total); break;
+        case 2: cm::gather_rows_kernel<uint16_t><<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, perm, n_src, n_dst, (int)cpr, total); break;
+        default: cm::gather_rows_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, perm, n_src, n_dst, (int)cpr, total); break;
+    }
+    return (int)cudaGetLastError();
+}

@@ -2,7 +2,9 @@
 
 The reference chains four einops rearranges per call.  The transform is a fixed permutation of the
 h*w token positions, so here it is computed ONCE per (h, w, chunk sizes, device) as an index vector
-and applied with a single gather (`index_select`), as is its inverse.
+and applied with a single gather, as is its inverse: CUDA tensors go through the library's gather
+kernel (cm_gather_rows), CPU tensors (the reference also calls these on host-side tables at set-up time) through
+torch.index_select.
 """
 from __future__ import annotations
 
@@ -34,7 +36,16 @@ def _perm(h: int, w: int, c1: int, c2: int, device: str):
     perm = torch.empty(h * w, dtype=torch.long, device=dev)
     perm[key.reshape(-1)] = torch.arange(h * w, device=dev)
     inv = key.reshape(-1).clone()
+    if dev.type == "cuda":
+        return perm.to(torch.int32), inv.to(torch.int32)
     return perm, inv
+
+
+def _gather(x: torch.Tensor, dim: int, perm: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        from .. import torch_ops as _t
+        return _t.gather_rows(x, dim, perm)
+    return x.index_select(dim, perm)
 
 
 def patchify(x: torch.Tensor) -> torch.Tensor:
@@ -43,7 +54,7 @@ def patchify(x: torch.Tensor) -> torch.Tensor:
     b, h, w = x.shape
     c1, c2 = _chunks()
     perm, _ = _perm(h, w, c1, c2, str(x.device))
-    return x.reshape(b, h * w).index_select(1, perm)
+    return _gather(x.reshape(b, h * w), 1, perm)
 
 
 def unpatchify(x_chunk_flat: torch.Tensor, original_shape) -> torch.Tensor:
@@ -51,7 +62,7 @@ def unpatchify(x_chunk_flat: torch.Tensor, original_shape) -> torch.Tensor:
     b, h, w = original_shape
     c1, c2 = _chunks()
     _, inv = _perm(h, w, c1, c2, str(x_chunk_flat.device))
-    return x_chunk_flat.index_select(1, inv).reshape(x_chunk_flat.shape[0], h, w)
+    return _gather(x_chunk_flat, 1, inv).reshape(x_chunk_flat.shape[0], h, w)
 
 
 def patchify_rope(x_shape, pe: torch.Tensor, width_rope: int, height_rope: int) -> torch.Tensor:
@@ -61,5 +72,5 @@ def patchify_rope(x_shape, pe: torch.Tensor, width_rope: int, height_rope: int) 
     c1, c2 = _chunks()
     perm, _ = _perm(height_rope, width_rope, c1, c2, str(pe.device))
     tail = pe[:, :, -img_tokens:]
-    pe[:, :, -img_tokens:] = tail.index_select(2, perm)
+    pe[:, :, -img_tokens:] = _gather(tail, 2, perm)
     return pe

@@ -3,7 +3,8 @@
 
 `voxel_chunk_no_padding` groups tokens of a [t, h, w] latent into vt x vh x vw voxels (so that a
 192-token query group is spatially compact) and appends the ragged tails in raster order; like the
-2-D patching it is a fixed permutation, built once per shape and applied with one gather.
+2-D patching it is a fixed permutation, built once per shape and applied with one gather (the library's
+cm_gather_rows kernel for CUDA tensors: 256-byte token rows, coalesced both ways; torch.index_select for CPU tensors).
 """
 from __future__ import annotations
 
@@ -31,20 +32,29 @@ def _voxel_perm(t: int, h: int, w: int, vt: int, vh: int, vw: int, device: str):
     perm = torch.cat([o.reshape(-1) for o in order])
     inv = torch.empty_like(perm)
     inv[perm] = torch.arange(perm.numel(), device=dev)
+    if dev.type == "cuda":
+        return perm.to(torch.int32), inv.to(torch.int32)
     return perm, inv
+
+
+def _gather(x: torch.Tensor, dim: int, perm: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        from .. import torch_ops as _t
+        return _t.gather_rows(x, dim, perm)
+    return x.index_select(dim, perm)
 
 
 def voxel_chunk_no_padding(x: torch.Tensor, voxel_shape=(4, 4, 4)) -> torch.Tensor:
     """x [b, ah, t, h, w, d] -> [b, ah, t*h*w, d] in voxel order (tails appended)."""
     b, ah, t, h, w, d = x.shape
     perm, _ = _voxel_perm(t, h, w, *voxel_shape, str(x.device))
-    return x.reshape(b, ah, t * h * w, d).index_select(2, perm)
+    return _gather(x.reshape(b, ah, t * h * w, d), 2, perm)
 
 
 def reverse_voxel_chunk_no_padding(x_chunk_flat: torch.Tensor, original_shape, voxel_shape=(4, 4, 4)) -> torch.Tensor:
     b, ah, t, h, w, d = original_shape
     _, inv = _voxel_perm(t, h, w, *voxel_shape, str(x_chunk_flat.device))
-    return x_chunk_flat.index_select(2, inv).reshape(b, ah, t, h, w, d)
+    return _gather(x_chunk_flat, 2, inv).reshape(b, ah, t, h, w, d)
 
 
 def masktoinds(mask: torch.Tensor, multiple=None):

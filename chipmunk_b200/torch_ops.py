@@ -381,6 +381,28 @@ def select_columns(cs, k: int, multiple_of: int, random_prob: float = 0.0, stati
     return packed, torch.Size((B, H, G, n)), indices, counts
 
 
+def gather_rows(x: torch.Tensor, dim: int, perm: torch.Tensor) -> torch.Tensor:
+    """x.index_select(dim, perm) for a CUDA tensor, as ONE gather kernel (cm_gather_rows): the token reorderings of
+    chipmunk.ops.patch / chipmunk.ops.voxel.  `perm` int32 on the same device."""
+    require_cuda(x, perm)
+    _chk(perm.dtype == torch.int32 and perm.is_contiguous() and perm.dim() == 1, "gather_rows: perm must be contiguous int32 [n]")
+    dim = dim % x.dim()
+    x = x.contiguous()
+    outer = 1
+    for d in x.shape[:dim]:
+        outer *= int(d)
+    inner = x.element_size()
+    for d in x.shape[dim + 1:]:
+        inner *= int(d)
+    n_src, n_dst = int(x.shape[dim]), int(perm.numel())
+    out = torch.empty((*x.shape[:dim], n_dst, *x.shape[dim + 1:]), dtype=x.dtype, device=x.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        check(lib.cm_gather_rows(_ptr(x), _ptr(out), _ptr(perm), outer, n_src, n_dst, inner, stream_ptr(x.device)), "gather_rows")
+    return out
+
+
 def bitpack(mask):
     require_cuda(mask)
     _chk(mask.dtype == torch.bool, "mask must be bool type")

@@ -188,6 +188,13 @@ int cm_topk_indices(const void* act, int dtype, int32_t* indices, int32_t* count
 int cm_copy_indices(const void* src, void* dst, int elem_size, const int32_t* indices,
                     const int32_t* counts, int B, int M, int Rr, int F, void* stream);
 
+/* Token reordering: dst[o, i, :] = src[o, perm[i], :] for o < outer, i < n_dst; rows of row_bytes bytes, src has n_src
+ * rows per outer index.  One gather replaces the chains of einops rearranges of the reference's 2-level patchify
+ * (src/chipmunk/ops/patch.py:7-80) and 3-D voxel chunking (src/chipmunk/ops/voxel.py:9-99); the permutation itself is
+ * built once per shape on the host side (chipmunk_b200/ops/{patch,voxel}.py). */
+int cm_gather_rows(const void* src, void* dst, const int32_t* perm, int64_t outer, int64_t n_src, int64_t n_dst,
+                   int64_t row_bytes, void* stream);
+
 /* Replace bitpack / bitunpack (src/chipmunk/ops/bitpack.py:4-69): n mask bytes <-> ceil(n/8)
  * packed bytes, little-endian bit order. */
 int cm_bitpack(const uint8_t* mask, uint8_t* packed, int64_t n, void* stream);
