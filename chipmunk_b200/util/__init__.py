@@ -3,6 +3,7 @@ Mirrors the names exported by the reference's `chipmunk.util` (src/chipmunk/util
 from .config import GLOBAL_CONFIG, BASE_CONFIG, load_from_file, update_global_config
 from .layer_counter import LayerCounter
 from .storage import AttnStorage, MlpStorage, LayerStorage, MaybeOffloadedTensor, PIPELINE_DEPTH
+from .step_cache import StepCache
 
 __all__ = ["GLOBAL_CONFIG", "BASE_CONFIG", "load_from_file", "update_global_config", "LayerCounter",
-           "AttnStorage", "MlpStorage", "LayerStorage", "MaybeOffloadedTensor", "PIPELINE_DEPTH"]
+           "AttnStorage", "MlpStorage", "LayerStorage", "MaybeOffloadedTensor", "PIPELINE_DEPTH", "StepCache"]

@@ -4,7 +4,8 @@
 B200 difference: `offloading.global_disable_offloading` defaults to True.  The reference moves
 each layer's caches to pinned host memory because an 80 GB H100 cannot hold them (731 MB per
 layer x 60 layers at HunyuanVideo 720p); 180 GB of HBM3e can, so caches stay resident unless a
-config file turns offloading back on.
+config file turns offloading back on -- and then `offloading.backing: peer` parks them in a neighbour GPU's HBM over
+NVLink instead of in host memory (util/storage.py).
 """
 from __future__ import annotations
 
@@ -51,6 +52,11 @@ BASE_CONFIG: Dict[str, Any] = {
     },
     "offloading": {
         "global_disable_offloading": True,
+        # B200 addition: where an offloaded cache lives.  "host" = pinned host memory (the reference's only option,
+        # PCIe ~55 GB/s); "peer" = the HBM of another GPU of the NVSwitch domain (`peer_device`, NVLink ~770 GB/s per
+        # direction): the residency manager for configurations whose caches exceed one GPU's 180 GB
+        "backing": "host",
+        "peer_device": None,
         "mlp.out_cache": False,
         "mlp.indices": False,
         "mlp.counts": False,

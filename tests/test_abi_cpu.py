@@ -149,3 +149,28 @@ def test_parallel_shards_and_fused_guard(cm):
     assert parallel.shard_heads(24, 8, 3) == (9, 12)
     assert parallel.shard_heads(7, 2, 0) == (0, 4) and parallel.shard_heads(7, 2, 1) == (4, 7)
     assert callable(parallel.sparse_attention_head_parallel_fused)
+
+
+def test_step_cache_glue(cm):
+    """StepCache reproduces the reference's step-caching glue (examples/hunyuan/hyvideo/modules/models.py:732-741,834-835):
+    skipped steps return the stored output and advance the layer counter's inference step."""
+    from chipmunk_b200.util import StepCache, LayerCounter
+    from chipmunk_b200.util.config import reset_to_defaults, GLOBAL_CONFIG
+    reset_to_defaults()
+    sc = StepCache()
+    counter = LayerCounter(num_layers=1, num_sparse_submodules_per_layer=1)
+    assert sc.try_skip(0, counter) is None and counter.cur_inference_step == 0
+    x = torch.arange(12.0).reshape(3, 4)
+    sc.store(x)
+    x += 1                                              # the cache holds a copy, like the reference's clone()
+    assert 7 in GLOBAL_CONFIG["step_caching"]["skip_step_schedule"]
+    got = sc.try_skip(7, counter)
+    assert torch.equal(got, torch.arange(12.0).reshape(3, 4)) and counter.cur_inference_step == 1
+    assert sc.try_skip(8, counter) is None and counter.cur_inference_step == 1
+    GLOBAL_CONFIG["step_caching"]["is_enabled"] = False
+    assert sc.try_skip(7, counter) is None
+    sc.reset()
+    GLOBAL_CONFIG["step_caching"]["is_enabled"] = True
+    with pytest.raises(RuntimeError):
+        sc.try_skip(7, counter)
+    reset_to_defaults()
