@@ -148,3 +148,40 @@ def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads:
         return out.permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
     o = _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1)
     return all_gather_heads(o, num_heads, group)
+
+
+class HeadParallelAttn:
+    """`SparseDiffAttn` for one rank's heads of a head-parallel layer (the reference's multi-GPU HunyuanVideo mode,
+    hyvideo/modules/head_parallel.py:42-115 + attenion.py:229-292, with ONE gather of O per step instead of two
+    all_to_all + all_gather).  q, k, v hold this rank's heads [B, H / world, N, D]; the call returns all heads [B, H, N, D].
+
+    * sparse steps: the module's stored mask -> indices, then `sparse_attention_head_parallel`: the delta-attention kernel
+      writes cache + delta straight into every GPU's copy of the output (NVLS multicast epilogue; NCCL all-gather fallback);
+    * full steps: dense (+ column sums, selection, cache build) run on the local heads -- every tile of the path is
+      independent given its head's K/V, so nothing is exchanged -- and the dense output is gathered with one
+      in-place ncclAllGather (the dense kernel's TMA store writes directly into this rank's slice of the gather buffer).
+    """
+
+    def __init__(self, attn_module, num_heads: int, group=None):
+        self.attn = attn_module
+        self.num_heads = num_heads
+        self.group = group
+
+    def __call__(self, q, k, v):
+        from .util import GLOBAL_CONFIG
+        from . import ops
+
+        attn, cfg = self.attn, GLOBAL_CONFIG["attn"]
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1 or not cfg["is_enabled"]:
+            return attn(q, k, v)
+        counter = attn.layer_counter
+        full = counter.should_do_full_attn_step() or attn.layer_num < cfg["first_n_dense_layers"]
+        if full:
+            o_local = attn(q, k, v)                                   # advances the counter itself
+            return all_gather_heads(o_local, self.num_heads, self.group)
+        multiple_of = 128 if cfg["pad_qkv_before_kernel"] else cfg["counts_multiple_of"]
+        inds, counts = attn._stored_indices(multiple_of, cfg["mbm"])
+        out = sparse_attention_head_parallel(q, k, v, attn.storage.get_out_cache(), inds, counts, self.num_heads, self.group)
+        counter.increment()
+        return out

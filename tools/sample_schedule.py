@@ -27,7 +27,18 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    # under torchrun: BASELINE.json configs[3], the schedule with the layer head-parallel over the GPUs of one box
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        assert a.heads % world == 0
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    total_heads = a.heads
+    a.heads = a.heads // world
     GLOBAL_CONFIG["steps"] = a.steps
     GLOBAL_CONFIG["attn"].update({"is_enabled": True, "top_keys": 0.05, "random_keys": 0.01, "local_voxels": 0,
                                   "local_1d_window": 0, "first_n_dense_layers": 2, "recompute_mask": True,
@@ -36,8 +47,11 @@ def main():
     GLOBAL_CONFIG["mlp"]["is_enabled"] = False
     counter = LayerCounter(num_layers=1, num_sparse_submodules_per_layer=1)
     layer = cm.SparseDiffAttn(layer_num=2, layer_counter=counter)        # layer_num >= first_n_dense_layers
+    if world > 1:
+        from chipmunk_b200.parallel import HeadParallelAttn
+        layer = HeadParallelAttn(layer, total_heads)
 
-    g = torch.Generator(device=dev).manual_seed(0)
+    g = torch.Generator(device=dev).manual_seed(rank)
     q, k, v = (torch.randn(1, a.heads, a.seq, 128, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
     times, kinds = [], []
     for step in range(a.steps - 1):          # the reference's odometer rewinds before the last coordinate
@@ -47,7 +61,12 @@ def main():
         o = layer(q, k, v)
         e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        times.append(ms)
         kinds.append("full" if full else "sparse")
         del o
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,17 +80,22 @@ def main():
     t_dense = e0.elapsed_time(e1) / 3
     full_ms = [t for t, kd in zip(times, kinds) if kd == "full"]
     sparse_ms = [t for t, kd in zip(times, kinds) if kd == "sparse"]
-    res = {"workload": "one attention layer through a 49-step HunyuanVideo schedule (full steps 0,1,10,40; recompute_mask; packed indices)",
-           "seq": a.seq, "heads": a.heads, "n_full": len(full_ms), "n_sparse": len(sparse_ms),
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    res = {"n_gpus": world, "workload": "one attention layer through a 49-step HunyuanVideo schedule (full steps 0,1,10,40; recompute_mask; packed indices)",
+           "seq": a.seq, "heads": total_heads, "heads_per_gpu": a.heads, "n_full": len(full_ms), "n_sparse": len(sparse_ms),
            "full_step_ms": [round(t, 2) for t in full_ms],
            "sparse_step_ms_median": round(sorted(sparse_ms)[len(sparse_ms) // 2], 3),
            "sparse_step_ms_minmax": [round(min(sparse_ms), 3), round(max(sparse_ms), 3)],
-           "layer_total_ms": round(sum(times), 1), "dense_sdpa_ms_per_step": round(t_dense, 2),
+           "layer_total_ms": round(sum(times), 1), "dense_sdpa_ms_per_step": round(t_dense, 2),   # cuDNN SDPA on the same (per-GPU) heads
            "dense_total_ms": round(t_dense * len(times), 1), "speedup_vs_dense_sdpa": round(t_dense * len(times) / sum(times), 2)}
     print(json.dumps(res))
     if a.out:
         with open(a.out, "w") as f:
             f.write(json.dumps(res) + "\n")
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
