@@ -259,7 +259,10 @@ def run_ours(args):
             traffic_db = json.load(f)
     # the attention launch of THIS rank (hl heads); at N > 1 its time includes the multicast / NCCL gather of O
     roofline = _roof(attn_alg_bytes(hl, n, count), t_attn, hbm_gbs, peak_src, traffic_db.get("c3_csp_attn_add") if world == 1 else None)
-    roofline.update({"kernel": "attn::attn_kernel<false> (csp_attn_add)" + (" + fused multicast gather of O" if use_fused else (" + ncclAllGather" if world > 1 else "")),
+    roofline.update({"note": "SURVEY 8d gather roofline: algorithmic indexed-KV bytes / HBM peak.  `traffic` (ncu DRAM bytes per launch) is ~7x "
+                             "smaller: a head's K/V (61 MB) stays in the 126 MB L2 under head-major tile order, so the gather is served by L2 "
+                             "and the kernel is bound by its S -> softmax -> P.V chain (tensor pipe 63 % active), not by HBM",
+                     "kernel": "attn::attn_kernel<false> (csp_attn_add)" + (" + fused multicast gather of O" if use_fused else (" + ncclAllGather" if world > 1 else "")),
                      "launch_us": round(t_attn * 1e3, 1), "algorithmic_bytes_per_launch": attn_alg_bytes(hl, n, count),
                      "tensor_tflops": round(4.0 * QG * count * D * hl * G / (t_attn * 1e-3) / 1e12, 1),
                      "tensor_frac_of_burst_peak": round(4.0 * QG * count * D * hl * G / (t_attn * 1e-3) / 1e12 / tf_burst, 4)})

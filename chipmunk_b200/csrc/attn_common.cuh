@@ -1,4 +1,4 @@
-// Pieces shared by the 1-CTA and 2-CTA attention kernels.
+// Softmax steps of the column-sparse attention kernel (csp_attn.cu).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -135,81 +135,6 @@ __device__ __forceinline__ void softmax_step_narrow(uint32_t tS, uint32_t tO, in
     }
     tmem_st_32x32b_x16(tS, pk);
     l_sum += acc;
-}
-
-// Half-row variant: TWO threads (same TMEM lane, two warps of the same lane quadrant) share a query row,
-// thread `hf` owning key columns [64 hf, 64 hf + 64) of the step and head dims [64 hf, 64 hf + 64) of O.
-// One warp per SM sub-partition cannot hide the exp2/convert latencies of a 128-column row; two can.
-// The tile maximum is exchanged through shared memory (mx_w / mx_r, double-buffered by the caller)
-// with a 64-thread named barrier; both threads then take identical rescale decisions, so m_ref stays
-// equal in the pair while l_sum is a per-thread partial sum (added up in the epilogue).
-template <bool TAIL>
-__device__ __forceinline__ void softmax_half_step(uint32_t tS, uint32_t tO, int hf, int valid, int kk, float& m_ref,
-                                                  float& l_sum, float* mx_w, const float* mx_r, uint32_t bar_id) {
-    constexpr int HC = KT / 2;
-    uint32_t s[HC];
-    tmem_ld32(tS + hf * HC, s);
-    tmem_ld32(tS + hf * HC + 32, s + 32);
-    tmem_ld_wait();
-    if (TAIL) {
-#pragma unroll
-        for (int j = 0; j < HC; j++) s[j] = (hf * HC + j < valid) ? s[j] : 0xff800000u;
-    }
-    float mx[2];
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-        mx[c] = __uint_as_float(s[c * 32]);
-#pragma unroll
-        for (int j = 1; j < 31; j += 2)
-            mx[c] = fmax3(mx[c], __uint_as_float(s[c * 32 + j]), __uint_as_float(s[c * 32 + j + 1]));
-        mx[c] = fmaxf(mx[c], __uint_as_float(s[c * 32 + 31]));
-    }
-    const float m_part = fmaxf(mx[0], mx[1]);
-    *mx_w = m_part;
-    named_bar_sync(bar_id, 64);          // also orders both threads' S loads before either one's P stores
-    const float m_tile = fmaxf(m_part, *mx_r);
-    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
-    if (__any_sync(0xffffffffu, need)) {
-        float alpha = 1.f;
-        if (need) {
-            alpha = fast_exp2((m_ref - m_tile) * SCALE_LOG2);
-            m_ref = m_tile;
-            l_sum *= alpha;
-        }
-        if (kk > 0) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < HC; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tO + hf * HC + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-                tmem_st_32x32b_x32(tO + hf * HC + c0, r);
-            }
-        }
-    }
-    const float neg_m = -m_ref * SCALE_LOG2;
-    const uint64_t c2 = pack_f32x2(SCALE_LOG2, SCALE_LOG2), nm2 = pack_f32x2(neg_m, neg_m);
-    uint64_t acc[2] = {0ull, 0ull};
-    const int cols = TAIL ? ((valid + 15) & ~15) : KT;
-#pragma unroll
-    for (int c0 = 0; c0 < HC; c0 += 32) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const uint64_t x = ffma2(pack_f32x2(__uint_as_float(s[c0 + j]), __uint_as_float(s[c0 + j + 1])), c2, nm2);
-            float x0, x1;
-            unpack_f32x2(x, x0, x1);
-            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-            acc[(j >> 1) & 1] = fadd2(acc[(j >> 1) & 1], pack_f32x2(p0, p1));
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-        }
-        if (!TAIL || hf * HC + c0 < cols) tmem_st_32x32b_x16(tS + ((hf * HC + c0) >> 1), pk);
-    }
-    float a0, a1, a2, a3;
-    unpack_f32x2(acc[0], a0, a1);
-    unpack_f32x2(acc[1], a2, a3);
-    l_sum += (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace attn

@@ -1,7 +1,7 @@
-// Column-sparse "delta" attention and dense attention (+ column sums) for sm_100a.
+// Column-sparse "delta" attention for sm_100a.
 //
-// Replaces csrc/attn/{csp_attn,csp_128_attn,dense_attn,dense_colsum_attn}.cu of the reference
-// (Hopper wgmma + ThunderKittens) with one warp-specialised tcgen05 kernel template.
+// Replaces csrc/attn/{csp_attn,csp_128_attn}.cu of the reference (Hopper wgmma + ThunderKittens) with one
+// warp-specialised tcgen05 kernel.  (The dense full-step operators live in dense_attn.cu.)
 //
 // Work unit ("tile"): one (batch, head, group of 192 query rows).  Per tile the kernel walks the
 // group's selected key columns 128 at a time:
@@ -13,7 +13,7 @@
 //     softmax warps (4+2)  one thread per query row: TMEM -> regs, running max with lazy
 //                          rescale, exp2, row sum, P (bf16) written back over S in TMEM,
 //     epilogue             (same threads) O / l * o_scale -> bf16, optional add of the cached
-//                          output tile, store.  Dense mode also writes l and the column sums.
+//                          output tile, store.
 // The two query blocks ping-pong on the tensor pipe: while the softmax warps of block 0 work on
 // S0(k), the pipe runs S1(k) / P1 V(k-1), and vice versa.
 //
@@ -34,21 +34,18 @@ namespace attn {
 
 constexpr int NSLOT = 5;            // 32 KB K/V slots
 constexpr int SLOT_BYTES = KT * D * 2;
-// Per-variant geometry.  The column-sparse kernel works on the reference's 192-query index groups (block 1 is half
-// empty: an M=128 MMA for 64 rows).  Dense attention has no index groups, so its tiles are 256 queries = two FULL
-// M=128 blocks: a third more rows for the same tensor time, 8 softmax warps (2 per SM sub-partition).
-template <bool DENSE> struct Geo {
-    static constexpr int QROWS = DENSE ? 256 : QG;               // query rows per tile
+// Geometry: the reference's 192-query index groups = one full M=128 block + one half-empty one (an M=128 MMA for 64 rows).
+struct GEO {
+    static constexpr int QROWS = QG;                             // query rows per tile
     static constexpr int Q_HALF_BYTES = QROWS * 128;             // one 64-wide d-half of the Q tile
-    static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB / 64 KB
+    static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB
     static constexpr int SMEM_BYTES = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
-    // sparse: warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
-    // dense : warps 0-3 softmax blk0 | 4-7 softmax blk1 | 8-11 producers | 12 MMA, 13-15 idle
-    static constexpr int NUM_THREADS = DENSE ? 512 : 384;
-    static constexpr int WARP_MMA = DENSE ? 12 : 6;
-    static constexpr int NUM_SOFTMAX_WARPS = DENSE ? 8 : 6;
-    static constexpr int REG_SOFTMAX = DENSE ? 200 : 208;        // setmaxnreg budgets: 64 K registers per SM
-    static constexpr int REG_OTHER = DENSE ? 56 : 80;
+    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
+    static constexpr int NUM_THREADS = 384;
+    static constexpr int WARP_MMA = 6;
+    static constexpr int NUM_SOFTMAX_WARPS = 6;
+    static constexpr int REG_SOFTMAX = 208;                      // setmaxnreg budgets: 64 K registers per SM
+    static constexpr int REG_OTHER = 80;
 };
 constexpr int WARP_PROD0 = 8;
 constexpr int NUM_PROD = 128;
@@ -61,9 +58,8 @@ struct Params {
     const __nv_bfloat16* k;
     const __nv_bfloat16* v;
     __nv_bfloat16* o;
-    const int32_t* indices;      // null in dense mode
-    const int32_t* counts;       // null in dense mode
-    float* l;                    // dense mode: [B,H,Nq]
+    const int32_t* indices;
+    const int32_t* counts;
     const __nv_bfloat16* cache;  // fused add-back: o = bf16(cache + o_scale * delta), out of place (null: see `accumulate`)
     int B, H, Nq, Nk, G;
     int64_t qs[3], ks[3], vs[3], os[3], cs[3];
@@ -82,17 +78,14 @@ struct __align__(8) Barriers {
     uint64_t s_full[2], p_full[2], o_full[2];
 };
 
-__device__ __forceinline__ int tile_count(const Params& P, int tile, bool dense) {
-    if (dense) return P.Nk;
+__device__ __forceinline__ int tile_count(const Params& P, int tile) {
     int c = __ldg(P.counts + tile);
     c = c < 0 ? 0 : c;
     return c > (int)P.idx_row_stride ? (int)P.idx_row_stride : c;
 }
 
 // ------------------------------------------------------------------------------------------
-template <bool DENSE>
-__global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const Params P) {
-    using GEO = Geo<DENSE>;
+__global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params P) {
     constexpr int QROWS = GEO::QROWS, Q_HALF_BYTES = GEO::Q_HALF_BYTES, Q_BYTES = GEO::Q_BYTES, WARP_MMA = GEO::WARP_MMA;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
@@ -129,7 +122,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
         uint32_t job = 0;                           // K/V slot fills issued so far
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
-            const int count = tile_count(P, tile, DENSE);
+            const int count = tile_count(P, tile);
             if (count <= 0) { it--; continue; }
             const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
             // ---- Q tile (192 rows, zero-filled past Nq)
@@ -148,7 +141,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
             }
             const __nv_bfloat16* kb = P.k + b * P.ks[0] + h * P.ks[1];
             const __nv_bfloat16* vb = P.v + b * P.vs[0] + h * P.vs[1];
-            const int32_t* ip = DENSE ? nullptr : P.indices + (int64_t)tile * P.idx_row_stride;
+            const int32_t* ip = P.indices + (int64_t)tile * P.idx_row_stride;
             const int nk = (count + KT - 1) / KT;
             // Lane j of producer warp w fetches the index of key row (2w + (j>>4)) + 8*(j&15) of the
             // step: one coalesced-ish load per thread per step, issued one step ahead; the 16 rows a
@@ -158,7 +151,6 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
             // the load at the fetch and defeat the one-step-ahead prefetch); fix_idx clamps it at the use site
             auto fetch_idx = [&](int kk) -> int {
                 const int pos = kk * KT + my_r;
-                if (DENSE) return pos;
                 return pos < count ? __ldg(ip + pos) : 0;
             };
             auto fix_idx = [&](int kk, int idx) -> int {
@@ -196,7 +188,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
-        if (DENSE) setmaxnreg_dec<GEO::REG_OTHER>(); else setmaxnreg_inc<GEO::REG_SOFTMAX>();   // warpgroup-wide: sparse shares WG1 with softmax warps
+        setmaxnreg_inc<GEO::REG_SOFTMAX>();   // warpgroup-wide: the MMA warp shares warpgroup 1 with softmax warps
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
         const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
@@ -206,7 +198,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
         // (`lane == 0`) it wraps each one in an ELECT / branch loop (~25 cycles per MMA, ~800 per step) during which
         // the tensor pipe drains.
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, it++) {
-            const int count = tile_count(P, tile, DENSE);
+            const int count = tile_count(P, tile);
             if (count <= 0) { it--; continue; }
             const int nk = (count + KT - 1) / KT;
             auto ncols = [&](int kk) { int v = count - kk * KT; v = v > KT ? KT : v; return (v + 15) & ~15; };
@@ -299,13 +291,13 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
         uint32_t sc = 0, oc = 0;
 
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-            const int count = tile_count(P, tile, DENSE);
+            const int count = tile_count(P, tile);
             const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
             const int row = g * QROWS + r_in_tile;
             const bool row_ok = row < P.Nq;
             __nv_bfloat16* orow = P.o + b * P.os[0] + h * P.os[1] + (int64_t)(row_ok ? row : 0) * P.os[2];
             if (count <= 0) {
-                if (!DENSE && P.cache != nullptr) {
+                if (P.cache != nullptr) {
                     if (row_ok) {
                         const uint4* crow = reinterpret_cast<const uint4*>(P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)row * P.cs[2]);
 #pragma unroll
@@ -339,7 +331,7 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
             }
             // ---- epilogue: O / l * scale (+ cached o) -> bf16
             // fused add-back: this row of the cached output is requested before the last P.V lands
-            const bool fused = !DENSE && P.cache != nullptr;
+            const bool fused = P.cache != nullptr;
             const __nv_bfloat16* crow = P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)(row_ok ? row : 0) * P.cs[2];
             uint32_t cv[4][8];                         // half a row of the cache: 4 sectors of 32 bytes
             auto load_cache_half = [&](int hf) {
@@ -359,7 +351,6 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
             mbar_wait(&bar.o_full[blk], oc & 1); oc++;
             tc_fence_after_sync();
             const float inv = P.o_scale / l_sum;
-            if (DENSE && row_ok && P.l) P.l[(int64_t)bh * P.Nq + row] = 1.f / (fast_exp2(m_ref * SCALE_LOG2) * l_sum);
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
                 uint32_t r[64];
@@ -428,8 +419,8 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
         }
     }
     else {
-        // idle warps: setmaxnreg is warpgroup-wide (sparse: warp 7 in the softmax group; dense: warps 13-15 with the MMA warp)
-        if (DENSE) setmaxnreg_dec<GEO::REG_OTHER>(); else setmaxnreg_inc<GEO::REG_SOFTMAX>();
+        // idle warp 7: setmaxnreg is warpgroup-wide (it sits in the softmax group)
+        setmaxnreg_inc<GEO::REG_SOFTMAX>();
     }
 
     tc_fence_before_sync();
@@ -446,14 +437,12 @@ __global__ void __launch_bounds__(Geo<DENSE>::NUM_THREADS, 1) attn_kernel(const 
 using namespace cm;
 using namespace cm::attn;
 
-template <bool DENSE>
 static int launch_attn(Params& P, cudaStream_t stream) {
-    static unsigned long long configured = 0;          // one per template instance
-    auto kern = attn_kernel<DENSE>;
-    const int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(kern), Geo<DENSE>::SMEM_BYTES);
+    static unsigned long long configured = 0;
+    const int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn_kernel), GEO::SMEM_BYTES);
     if (rc) return rc;
     int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
-    kern<<<grid, Geo<DENSE>::NUM_THREADS, Geo<DENSE>::SMEM_BYTES, stream>>>(P);
+    attn_kernel<<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(P);
     return (int)cudaGetLastError();
 }
 
@@ -477,7 +466,7 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
     Params P{};
     P.q = (const __nv_bfloat16*)q; P.k = (const __nv_bfloat16*)k; P.v = (const __nv_bfloat16*)v;
     P.o = (__nv_bfloat16*)o;
-    P.indices = indices; P.counts = counts; P.l = nullptr;
+    P.indices = indices; P.counts = counts;
     P.cache = (const __nv_bfloat16*)cache;
     P.B = B; P.H = H; P.Nq = Nq; P.Nk = Nk; P.G = (Nq + QG - 1) / QG;
     for (int i = 0; i < 3; i++) {
@@ -497,7 +486,7 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
     P.dbg = debug_flags();
-    return launch_attn<false>(P, (cudaStream_t)stream);
+    return launch_attn(P, (cudaStream_t)stream);
 }
 
 extern "C" int cm_csp_attn(const void* q, const void* k, const void* v, void* o, const int32_t* indices,

@@ -8,7 +8,7 @@ timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/q_bench.err | tai
 cut -c1-400 gpurun_out/q_bench_n1.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/q_bench_ref.json
 M="gpu__time_duration.sum"
-timeout 900 ncu --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/q_launches.csv python bench.py --steps 4 --warmup 3 --no-extras > gpurun_out/q_launch_bench.log 2>&1
+timeout 900 ncu --metrics $M --clock-control none -k regex:"attn_kernel|mask_to_indices|mlp_kernel|dense_kernel|select_columns|bitpack|gather_rows" -c 400 --csv --log-file gpurun_out/q_launches.csv python bench.py --steps 4 --warmup 3 --no-extras > gpurun_out/q_launch_bench.log 2>&1
 X="--set full --import-source on --clock-control none --metrics l1tex__m_xbar2l1tex_read_bytes.sum,l1tex__m_xbar2l1tex_read_bytes.sum.per_second,l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read.sum.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum.per_second"
 timeout 900 ncu $X -k regex:"attn_kernel|mask_to_indices" -s 2 -c 2 -o gpurun_out/q_c3 -f python tools/prof_targets.py c3attn > gpurun_out/q_ncu_c3.log 2>&1; tail -1 gpurun_out/q_ncu_c3.log
 timeout 900 ncu $X -k regex:"attn_kernel|mlp_kernel" -s 6 -c 3 -o gpurun_out/q_c2 -f python tools/prof_targets.py c2 > gpurun_out/q_ncu_c2.log 2>&1; tail -1 gpurun_out/q_ncu_c2.log
