@@ -177,6 +177,31 @@ def _roof(alg_bytes, ms, hbm_gbs, peak_src, traffic=None, bound="hbm"):
             "traffic": traffic, "peak_source": peak_src}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE the pinned host buffers of the e2e
+    leg are allocated (first touch places them on that node).  With eight ranks on one box, staging buffers that all sit
+    on one socket make every H2D / D2H copy of the other socket's GPUs cross the inter-socket link (round 1: e2e got
+    slower with more GPUs).  Returns a short description for the JSON line; never fails the bench."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA affinity reported for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "note": repr(e)[:80]}
+
+
 # ---------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import chipmunk_b200 as cm  # noqa: F401  (registers torch.ops.chipmunk, loads the library: no fallback)
@@ -272,6 +297,7 @@ def run_ours(args):
                "csp_attn_add": {"us": round(t_attn * 1e3, 1), "gather_roofline_frac": roofline["frac"]}}
 
     # ---- e2e: the same step from pinned HOST buffers (q, k, v up; this rank's o down), H2D | compute | D2H streams
+    numa = bind_to_gpu_numa_node(local)
     host_in = [torch.empty(t.shape, dtype=bf).pin_memory() for t in (q, k, v)]
     for hb, t in zip(host_in, (q, k, v)):
         hb.copy_(t)
@@ -317,7 +343,7 @@ def run_ours(args):
     ms_e2e, _ = timed(1, lambda: e2e_run(e2e_steps))
     ms_e2e /= e2e_steps
     e2e = {"value": round(C3_DENSE_FLOPS / (ms_e2e * 1e-3) / 1e12, 2), "unit": "TFLOP/s-equiv",
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps, "host_numa": numa,
            "note": "q, k, v of every step uploaded from pinned host memory and o downloaded inside the timed region "
                    "(3 streams, double-buffered); PCIe-bound: %.2f GB per step and GPU" % ((h2d + d2h) / world / 1e9)}
     del inbuf, ostage, host_in, host_out

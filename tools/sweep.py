@@ -113,7 +113,7 @@ def main():
 
     sp = [0.50, 0.70, 0.82, 0.93]
     attention_sweep(dev, [4096, 16384] if a.quick else [4096, 16384, 65536, 119056], sp, hbm, emit)
-    mlp_sweep(dev, [4608] if a.quick else [4096, 4608, 16384], sp, hbm, emit)
+    mlp_sweep(dev, [4608] if a.quick else [4096, 4608, 16384, 119168], sp, hbm, emit)
     if a.out:
         with open(a.out, "w") as f:
             for d in lines:
