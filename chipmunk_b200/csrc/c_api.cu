@@ -137,6 +137,27 @@ int encode_tmap_4d_bf16_sw128(CUtensorMap* map, const void* base, const uint64_t
     return encode_cached(map, k);
 }
 
+int encode_tmap_bhnd(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t st[3], uint32_t box_rows, int8_t pos[3]) {
+    struct Dim { uint64_t size, stride; int role; } d[3] = {{(uint64_t)N, (uint64_t)st[2] * 2, 0}, {(uint64_t)H, (uint64_t)st[1] * 2, 1},
+                                                             {(uint64_t)B, (uint64_t)st[0] * 2, 2}};
+    auto key = [](const Dim& x) { return x.size == 1 ? ~0ull : x.stride; };
+    for (int i = 0; i < 3; i++)
+        for (int j = i + 1; j < 3; j++)
+            if (key(d[j]) < key(d[i])) { Dim t = d[i]; d[i] = d[j]; d[j] = t; }
+    uint64_t dims[4] = {128, 0, 0, 0}, strides[3];
+    uint32_t box[4] = {64, 1, 1, 1};
+    uint64_t prev = 256;
+    for (int i = 0; i < 3; i++) {
+        dims[i + 1] = d[i].size;
+        // a size-1 dimension's stride is never used for addressing; give it a valid monotone value
+        strides[i] = d[i].size == 1 ? prev : d[i].stride;
+        prev = strides[i] * d[i].size;
+        pos[d[i].role] = (int8_t)(i + 1);
+        if (d[i].role == 0) box[i + 1] = box_rows;
+    }
+    return encode_tmap_4d_bf16_sw128(m, base, dims, strides, box);
+}
+
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                         uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
     return cached_tmap_2d_bf16(map, base, rows, cols, pitch_bytes, box_cols, box_rows, swizzle_bytes);

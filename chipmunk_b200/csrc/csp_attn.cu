@@ -5,20 +5,24 @@
 //
 // Work unit ("tile"): one (batch, head, group of 192 query rows).  Per tile the kernel walks the
 // group's selected key columns 128 at a time:
+//     TMA thread           loads the dense Q tile and the cached output tile (4-D tensor maps: any batch / head / row
+//                          stride, rows past N read as zero), and stores / reduce-adds the finished output tile,
 //     producers (4 warps)  gather K[idx] / V[idx] rows (256 B each) with 16-byte cp.async into
-//                          128B-swizzled shared-memory slots (a 5-deep ring of 32 KB slots),
+//                          128B-swizzled shared-memory slots (a 4-deep ring of 32 KB slots),
 //     MMA warp (1 thread)  S = Q K^T   (tcgen05.mma SS, M=128 N<=128 K=128, fp32 in TMEM), twice:
 //                          query rows 0-127 ("block 0") and 128-191 ("block 1"),
 //                          O += P V    (tcgen05.mma TS: P read from TMEM, V as MN-major smem),
 //     softmax warps (4+2)  one thread per query row: TMEM -> regs, running max with lazy
 //                          rescale, exp2, row sum, P (bf16) written back over S in TMEM,
-//     epilogue             (same threads) O / l * o_scale -> bf16, optional add of the cached
-//                          output tile, store.
+//     epilogue             (same threads) O / l * o_scale -> bf16 (+ the cached tile, read from shared memory) into a
+//                          128B-swizzled staging tile that the TMA thread stores (csp_128_attn, csp_attn_add) or
+//                          reduce-adds at the L2 (csp_attn, like the reference's TMA store_add, csp_attn.cu:300).
 // The two query blocks ping-pong on the tensor pipe: while the softmax warps of block 0 work on
 // S0(k), the pipe runs S1(k) / P1 V(k-1), and vice versa.
 //
 // TMEM map (512 columns): S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512);  P aliases the
 // first 64 columns of its S.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,19 +32,21 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "attn_common.cuh"
+#include "tma.cuh"
 
 namespace cm {
 namespace attn {
 
-constexpr int NSLOT = 5;            // 32 KB K/V slots
+constexpr int NSLOT = 4;            // 32 KB K/V slots
 constexpr int SLOT_BYTES = KT * D * 2;
 // Geometry: the reference's 192-query index groups = one full M=128 block + one half-empty one (an M=128 MMA for 64 rows).
 struct GEO {
     static constexpr int QROWS = QG;                             // query rows per tile
     static constexpr int Q_HALF_BYTES = QROWS * 128;             // one 64-wide d-half of the Q tile
     static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB
-    static constexpr int SMEM_BYTES = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
-    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 idle | 8-11 producers
+    static constexpr int STAGE_BYTES = Q_BYTES;                  // 48 KB: the cached output tile in, the output tile out (TMA both ways)
+    static constexpr int SMEM_BYTES = Q_BYTES + STAGE_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
+    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 TMA (Q tile, cached tile, output tile) | 8-11 K/V gather producers
     static constexpr int NUM_THREADS = 384;
     static constexpr int WARP_MMA = 6;
     static constexpr int NUM_SOFTMAX_WARPS = 6;
@@ -68,6 +74,8 @@ struct Params {
     int accumulate;
     int wide;                    // o (and cache) rows are 32-byte aligned: the epilogue moves full sectors per access
     int64_t mc_delta;            // != 0: o lives in a symmetric buffer; rows are stored to (o + mc_delta bytes), its NVLS multicast alias
+    int stage;                   // 1: output (and cache) tiles go through shared memory and the TMA; 0: multicast epilogue (direct stores)
+    int8_t pos[3][3];            // coordinate slots of (row, head, batch) in the q / cache / o tensor maps
     int num_tiles;
     int dbg;                     // stage-isolation timing switches: only read in -DCM_DEBUG_STAGES builds (CM_DBG below)
 };
@@ -76,6 +84,7 @@ struct __align__(8) Barriers {
     uint64_t q_full, q_empty;
     uint64_t kv_full[NSLOT], kv_empty[NSLOT];
     uint64_t s_full[2], p_full[2], o_full[2];
+    uint64_t c_full, st_full, st_free;       // cached tile landed | staging tile written by the epilogue | read out by the TMA store
 };
 
 __device__ __forceinline__ int tile_count(const Params& P, int tile) {
@@ -85,7 +94,8 @@ __device__ __forceinline__ int tile_count(const Params& P, int tile) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params P) {
+__global__ void __launch_bounds__(GEO::NUM_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_o, const Params P) {
     constexpr int QROWS = GEO::QROWS, Q_HALF_BYTES = GEO::Q_HALF_BYTES, Q_BYTES = GEO::Q_BYTES, WARP_MMA = GEO::WARP_MMA;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Barriers bar;
@@ -94,10 +104,12 @@ __global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sQ = sbase;
-    const uint32_t sKV = sbase + Q_BYTES;
+    const uint32_t sStage = sbase + Q_BYTES;
+    const uint32_t sKV = sStage + GEO::STAGE_BYTES;
 
     if (tid == 0) {
-        mbar_init(&bar.q_full, NUM_PROD);
+        mbar_init(&bar.q_full, 1);
+        mbar_init(&bar.c_full, 1); mbar_init(&bar.st_full, QROWS); mbar_init(&bar.st_free, 1);
         mbar_init(&bar.q_empty, 1);
         for (int i = 0; i < NSLOT; i++) { mbar_init(&bar.kv_full[i], NUM_PROD); mbar_init(&bar.kv_empty[i], 1); }
         mbar_init(&bar.s_full[0], 1);  mbar_init(&bar.s_full[1], 1);
@@ -125,20 +137,6 @@ __global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params 
             const int count = tile_count(P, tile);
             if (count <= 0) { it--; continue; }
             const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
-            // ---- Q tile (192 rows, zero-filled past Nq)
-            mbar_wait(&bar.q_empty, (it & 1) ^ 1);
-            {
-                const __nv_bfloat16* qb = P.q + b * P.qs[0] + h * P.qs[1];
-#pragma unroll 4
-                for (int i = 0; i < QROWS / 8; i++) {
-                    const int r = rsub + 8 * i;
-                    const int row = g * QROWS + r;
-                    const bool ok = row < P.Nq;
-                    const __nv_bfloat16* src = qb + (ok ? row : 0) * P.qs[2] + chunk * 8;
-                    cp_async_16_zfill(sQ + half_off * Q_HALF_BYTES + r * 128 + ((c8 ^ (r & 7)) << 4), src, ok ? 16u : 0u);
-                }
-                cp_async_mbar_arrive_noinc(&bar.q_full);
-            }
             const __nv_bfloat16* kb = P.k + b * P.ks[0] + h * P.ks[1];
             const __nv_bfloat16* vb = P.v + b * P.vs[0] + h * P.vs[1];
             const int32_t* ip = P.indices + (int64_t)tile * P.idx_row_stride;
@@ -289,13 +287,33 @@ __global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params 
         const uint32_t tS = tm + (blk ? TM_S1 : TM_S0) + lane_off;
         const uint32_t tO = tm + (blk ? TM_O1 : TM_O0) + lane_off;
         uint32_t sc = 0, oc = 0;
+        uint32_t ti = 0;                                   // tiles of this CTA so far (phases of c_full / st_full / st_free)
+        const uint32_t sw = (uint32_t)(r_in_tile & 7);
+        const uint32_t srow = sStage + (uint32_t)r_in_tile * 128;     // this row in a d-half of the staging tile (halves 24 KB apart)
+        // the staging tile becomes writable: the cached tile has landed in it (fused add-back), or the previous tile's
+        // store has read it out
+        auto stage_ready = [&]() {
+            if (P.cache != nullptr) mbar_wait(&bar.c_full, ti & 1);
+            else if (ti > 0) mbar_wait(&bar.st_free, (ti - 1) & 1);
+        };
 
-        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ti++) {
             const int count = tile_count(P, tile);
             const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
             const int row = g * QROWS + r_in_tile;
             const bool row_ok = row < P.Nq;
             __nv_bfloat16* orow = P.o + b * P.os[0] + h * P.os[1] + (int64_t)(row_ok ? row : 0) * P.os[2];
+            if (count <= 0 && P.stage) {
+                // no contribution: the cached tile passes through as it is; a fresh output (or a delta to add) is zero
+                stage_ready();
+                if (P.cache == nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) st_shared_v4(srow + (c >> 3) * (GEO::STAGE_BYTES / 2) + ((((uint32_t)c & 7) ^ sw) << 4), 0, 0, 0, 0);
+                    fence_proxy_async_smem();
+                }
+                mbar_arrive(&bar.st_full);
+                continue;
+            }
             if (count <= 0) {
                 if (P.cache != nullptr) {
                     if (row_ok) {
@@ -330,6 +348,46 @@ __global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params 
                 mbar_arrive(&bar.p_full[blk]);
             }
             // ---- epilogue: O / l * scale (+ cached o) -> bf16
+            if (P.stage) {
+                // through shared memory and the TMA: no global load or store on the softmax threads.  The cached tile was
+                // TMA-loaded into the staging tile while this tile was being computed; the result overwrites it in place
+                // and the TMA thread stores (or reduce-adds) the tile.
+                const bool fused = P.cache != nullptr;
+                mbar_wait(&bar.o_full[blk], oc & 1); oc++;
+                tc_fence_after_sync();
+                const float inv = P.o_scale / l_sum;
+                stage_ready();
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    uint32_t r[64];
+                    tmem_ld32(tO + hf * 64, r);
+                    tmem_ld32(tO + hf * 64 + 32, r + 32);
+                    tmem_ld_wait();
+                    const uint32_t base = srow + hf * (GEO::STAGE_BYTES / 2);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            w[j] = pack_bf16x2(__uint_as_float(r[8 * c + 2 * j]) * inv, __uint_as_float(r[8 * c + 2 * j + 1]) * inv);
+                        const uint32_t a = base + (((uint32_t)c ^ sw) << 4);
+                        if (fused) {
+                            // o = bf16(cache + bf16(delta))
+                            const uint4 cv = ld_shared_v4(a);
+                            w[0] = pack_bf16x2(bf16_lo(cv.x) + bf16_lo(w[0]), bf16_hi(cv.x) + bf16_hi(w[0]));
+                            w[1] = pack_bf16x2(bf16_lo(cv.y) + bf16_lo(w[1]), bf16_hi(cv.y) + bf16_hi(w[1]));
+                            w[2] = pack_bf16x2(bf16_lo(cv.z) + bf16_lo(w[2]), bf16_hi(cv.z) + bf16_hi(w[2]));
+                            w[3] = pack_bf16x2(bf16_lo(cv.w) + bf16_lo(w[3]), bf16_hi(cv.w) + bf16_hi(w[3]));
+                        }
+                        st_shared_v4(a, w[0], w[1], w[2], w[3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                mbar_arrive(&bar.st_full);
+                continue;
+            }
+            // multicast epilogue (cm_csp_attn_add_bcast): direct stores to the NVLS alias of the symmetric output buffer
             // fused add-back: this row of the cached output is requested before the last P.V lands
             const bool fused = P.cache != nullptr;
             const __nv_bfloat16* crow = P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)(row_ok ? row : 0) * P.cs[2];
@@ -419,8 +477,54 @@ __global__ void __launch_bounds__(GEO::NUM_THREADS, 1) attn_kernel(const Params 
         }
     }
     else {
-        // idle warp 7: setmaxnreg is warpgroup-wide (it sits in the softmax group)
-        setmaxnreg_inc<GEO::REG_SOFTMAX>();
+        // =========================================================================== TMA thread (warp 7)
+        setmaxnreg_inc<GEO::REG_SOFTMAX>();        // warpgroup-wide: warp 7 sits in the softmax group
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_o);
+            uint32_t qn = 0;                        // Q tiles loaded so far
+            int tq = blockIdx.x;                    // first tile whose Q has not been requested yet
+            // request the Q tile of the next tile that has work (tiles with count 0 never touch Q)
+            auto next_q = [&]() {
+                while (tq < P.num_tiles && tile_count(P, tq) <= 0) tq += gridDim.x;
+                if (tq >= P.num_tiles) return;
+                const int g = tq % P.G, bh = tq / P.G, h = bh % P.H, b = bh / P.H;
+                if (qn > 0) mbar_wait(&bar.q_empty, (qn - 1) & 1);      // the previous Q tile has been consumed by its last S
+                mbar_arrive_expect_tx(&bar.q_full, Q_BYTES);
+                const TmaCoord c = tma_coords(P.pos[0], 0, g * QROWS, h, b);
+                tma_load_4d(sQ, &tm_q, &bar.q_full, 0, c.c[1], c.c[2], c.c[3]);
+                tma_load_4d(sQ + Q_HALF_BYTES, &tm_q, &bar.q_full, 64, c.c[1], c.c[2], c.c[3]);
+                qn++;
+                tq += gridDim.x;
+            };
+            next_q();
+            uint32_t ti = 0;
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ti++) {
+                const int g = tile % P.G, bh = tile / P.G, h = bh % P.H, b = bh / P.H;
+                if (P.stage && P.cache != nullptr) {
+                    // the staging tile is free (the previous store has been read out below): fetch this tile's cached rows
+                    mbar_arrive_expect_tx(&bar.c_full, GEO::STAGE_BYTES);
+                    const TmaCoord c = tma_coords(P.pos[1], 0, g * QROWS, h, b);
+                    tma_load_4d(sStage, &tm_c, &bar.c_full, 0, c.c[1], c.c[2], c.c[3]);
+                    tma_load_4d(sStage + GEO::STAGE_BYTES / 2, &tm_c, &bar.c_full, 64, c.c[1], c.c[2], c.c[3]);
+                }
+                if (tile_count(P, tile) > 0) next_q();                 // Q of the tile after this one, as soon as this one's last S is issued
+                if (P.stage) {
+                    mbar_wait(&bar.st_full, ti & 1);                    // the epilogue threads have written (and fenced) the output tile
+                    const TmaCoord c = tma_coords(P.pos[2], 0, g * QROWS, h, b);
+                    if (P.cache == nullptr && P.accumulate) {
+                        tma_reduce_add_4d(&tm_o, sStage, 0, c.c[1], c.c[2], c.c[3]);
+                        tma_reduce_add_4d(&tm_o, sStage + GEO::STAGE_BYTES / 2, 64, c.c[1], c.c[2], c.c[3]);
+                    } else {
+                        tma_store_4d(&tm_o, sStage, 0, c.c[1], c.c[2], c.c[3]);
+                        tma_store_4d(&tm_o, sStage + GEO::STAGE_BYTES / 2, 64, c.c[1], c.c[2], c.c[3]);
+                    }
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    mbar_arrive(&bar.st_free);
+                }
+            }
+            bulk_wait<0>();
+        }
     }
 
     tc_fence_before_sync();
@@ -439,10 +543,17 @@ using namespace cm::attn;
 
 static int launch_attn(Params& P, cudaStream_t stream) {
     static unsigned long long configured = 0;
-    const int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn_kernel), GEO::SMEM_BYTES);
+    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn_kernel), GEO::SMEM_BYTES);
     if (rc) return rc;
+    // tensor maps (cached per argument set): Q tile in, cached tile in, output tile out; boxes of 192 rows x 64 columns
+    CUtensorMap mq, mc, mo;
+    rc = encode_tmap_bhnd(&mq, P.q, P.B, P.H, P.Nq, P.qs, QG, P.pos[0]);
+    if (!rc) rc = encode_tmap_bhnd(&mo, P.o, P.B, P.H, P.Nq, P.os, QG, P.pos[2]);
+    if (!rc && P.cache) rc = encode_tmap_bhnd(&mc, P.cache, P.B, P.H, P.Nq, P.cs, QG, P.pos[1]);
+    if (rc) return rc;
+    if (!P.cache) { mc = mo; for (int i = 0; i < 3; i++) P.pos[1][i] = P.pos[2][i]; }
     int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
-    attn_kernel<<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(P);
+    attn_kernel<<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(mq, mc, mo, P);
     return (int)cudaGetLastError();
 }
 
@@ -482,6 +593,7 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
     P.wide = wide_ok(o, o_strides) && (!cache || wide_ok(cache, c_strides)) ? 1 : 0;
     if (mc_delta != 0 && (!cache || (mc_delta & 15))) return CM_EINVAL;
     P.mc_delta = mc_delta;
+    P.stage = mc_delta == 0 ? 1 : 0;
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;

@@ -76,15 +76,8 @@ struct __align__(8) Barriers {
     uint64_t p_full, pv_done, cs_full, cs_empty;
 };
 
-// coordinates (row, head, batch) placed at the positions the tensor map wants them
-struct Coord { int c[4]; };
-__device__ __forceinline__ Coord coords(const int8_t pos[3], int col, int row, int h, int b) {
-    Coord r;
-    r.c[0] = col;
-#pragma unroll
-    for (int i = 1; i < 4; i++) r.c[i] = pos[0] == i ? row : (pos[1] == i ? h : b);
-    return r;
-}
+using Coord = TmaCoord;
+__device__ __forceinline__ Coord coords(const int8_t pos[3], int col, int row, int h, int b) { return tma_coords(pos, col, row, h, b); }
 
 template <bool HAS_CS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -459,27 +452,8 @@ using namespace cm::dense;
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool st_ok(const int64_t s[3]) { return s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0 && s[2] >= D; }
 
-// [B,H,N,128] view with element strides st = {batch, head, row}: a 4-D tensor map whose outer dimensions are ordered by
-// ascending stride (size-1 dimensions last), boxes of 128 rows x 64 columns.  pos[] = where (row, head, batch) landed.
 static int make_map(CUtensorMap* m, const void* base, int B, int H, int N, const int64_t st[3], int8_t pos[3]) {
-    struct Dim { uint64_t size, stride; int role; } d[3] = {{(uint64_t)N, (uint64_t)st[2] * 2, 0}, {(uint64_t)H, (uint64_t)st[1] * 2, 1},
-                                                             {(uint64_t)B, (uint64_t)st[0] * 2, 2}};
-    auto key = [](const Dim& x) { return x.size == 1 ? ~0ull : x.stride; };
-    for (int i = 0; i < 3; i++)
-        for (int j = i + 1; j < 3; j++)
-            if (key(d[j]) < key(d[i])) { Dim t = d[i]; d[i] = d[j]; d[j] = t; }
-    uint64_t dims[4] = {(uint64_t)D, 0, 0, 0}, strides[3];
-    uint32_t box[4] = {64, 1, 1, 1};
-    uint64_t prev = D * 2;
-    for (int i = 0; i < 3; i++) {
-        dims[i + 1] = d[i].size;
-        // a size-1 dimension's stride is never used for addressing; give it a valid monotone value
-        strides[i] = d[i].size == 1 ? prev : d[i].stride;
-        prev = strides[i] * d[i].size;
-        pos[d[i].role] = (int8_t)(i + 1);
-        if (d[i].role == 0) box[i + 1] = 128;
-    }
-    return encode_tmap_4d_bf16_sw128(m, base, dims, strides, box);
+    return encode_tmap_bhnd(m, base, B, H, N, st, 128, pos);
 }
 
 extern "C" int cm_dense_attn_strided(const void* q, const void* k, const void* v, void* o, float* l, void* cs, const float* p,

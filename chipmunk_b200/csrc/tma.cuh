@@ -27,6 +27,10 @@ int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint6
 // (encoding costs microseconds on the host and the operands of a diffusion step recur), see c_api.cu.
 int encode_tmap_4d_bf16_sw128(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                               const uint32_t box[4]);
+// [B,H,N,128] bf16 view with element strides st = {batch, head, row}: a 4-D tensor map whose outer dimensions are ordered
+// by ascending stride (size-1 dimensions last), boxes of `box_rows` rows x 64 columns.  pos[] = the coordinate slot
+// (1..3) where (row, head, batch) landed: see tma_coords().
+int encode_tmap_bhnd(CUtensorMap* map, const void* base, int B, int H, int N, const int64_t st[3], uint32_t box_rows, int8_t pos[3]);
 // cached forms of the 2-D encoders (same arguments, same result)
 int cached_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                         uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
@@ -47,6 +51,20 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src_smem)
+                 : "memory");
+}
+// coordinates (row, head, batch) placed at the slots an encode_tmap_bhnd map wants them
+struct TmaCoord { int c[4]; };
+__device__ __forceinline__ TmaCoord tma_coords(const int8_t pos[3], int col, int row, int h, int b) {
+    TmaCoord r;
+    r.c[0] = col;
+#pragma unroll
+    for (int i = 1; i < 4; i++) r.c[i] = pos[0] == i ? row : (pos[1] == i ? h : b);
+    return r;
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(map),
                  "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src_smem)
                  : "memory");
 }

@@ -1,0 +1,21 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from chipmunk_b200 import torch_ops as T
+from bench import make_indices
+dev = torch.device("cuda", 0)
+def med(fn, n):
+    fn(); torch.cuda.synchronize(); ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+for H, N, count, n in ((24, 4608, 784, 50), (24, 16384, 1152, 20), (24, 119056, 8320, 7)):
+    g = torch.Generator(device=dev).manual_seed(0)
+    G = (N + 191) // 192
+    q, k, v, c = (torch.randn(1, H, N, 128, device=dev, generator=g).to(torch.bfloat16) for _ in range(4))
+    o = torch.empty_like(c)
+    idx = make_indices(H * G, N, count, g, dev).view(1, H, G, N)
+    cnt = torch.full((1, H, G), count, dtype=torch.int32, device=dev)
+    t = med(lambda: T.csp_attn_add(q, k, v, c, idx, cnt, 1, out=o), n)
+    print(f"{os.environ.get('CHIPMUNK_B200_LIB', 'current'):42s} N={N:6d} count={count:5d}: csp_attn_add {t * 1e3:9.1f} us", flush=True)
+    del q, k, v, c, o, idx, cnt
