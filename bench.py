@@ -364,7 +364,15 @@ def run_ours(args):
             step(fused=False)
         ms_nccl, _ = timed(max(3, min(steps, 10)), lambda: step(fused=False))
         t_alone = _time(lambda: T.csp_attn_add(q, k, v, o_cache, *T.bitmask_to_indices(packed, mshape, 128, QG), 1, out=o_local), 3, warm=1)
-        extras["head_parallel"] = {"default_path": "fused multicast epilogue (NVLS)" if use_fused else "NCCL all-gather (no NVLS multicast on this box)",
+        ms_peers = None
+        if parallel.fused_gather_available((world, 1, hl, n, D), bf, dev, None, mode="peers"):
+            full_p = step(fused="peers")
+            full_n = step(fused=False)
+            barrier()
+            assert torch.equal(full_p, full_n), "peer-store fused gather differs from the NCCL all-gather"
+            del full_p, full_n
+            ms_peers, _ = timed(max(3, min(steps, 10)), lambda: step(fused="peers"))
+        extras["head_parallel"] = {"layer_ms_fused_peer_stores": None if ms_peers is None else round(ms_peers, 3), "default_path": "fused multicast epilogue (NVLS)" if use_fused else "NCCL all-gather (no NVLS multicast on this box)",
                                    "layer_ms_default": round(ms_step, 3), "layer_ms_nccl_allgather": round(ms_nccl, 3),
                                    "kernels_only_ms_this_rank": round(t_alone, 3),
                                    "allgather_bytes_per_rank": o_local.numel() * 2,

@@ -33,6 +33,7 @@ def _load() -> C.CDLL:
         "cm_csp_attn": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, p64, p64, p64, p64, i64, i32, i32, vp], i32),
         "cm_csp_attn_add": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, p64, p64, p64, p64, p64, i64, i32, vp], i32),
         "cm_csp_attn_add_bcast": ([vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, p64, p64, p64, p64, p64, i64, i32, vp], i32),
+        "cm_csp_attn_add_peers": ([vp, vp, vp, vp, vp, p64, i32, vp, vp, i32, i32, i32, i32, p64, p64, p64, p64, p64, i64, i32, vp], i32),
         "cm_dense_attn": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp], i32),
         "cm_dense_attn_strided": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, p64, p64, p64, p64, i64, vp], i32),
         "cm_csp_mlp_mm1": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, vp], i32),
@@ -55,7 +56,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTS = ("cm_abi_version", "cm_sm_count", "cm_strerror", "cm_csp_attn", "cm_csp_attn_add", "cm_csp_attn_add_bcast", "cm_dense_attn", "cm_dense_attn_strided",
+EXPORTS = ("cm_abi_version", "cm_sm_count", "cm_strerror", "cm_csp_attn", "cm_csp_attn_add", "cm_csp_attn_add_bcast", "cm_csp_attn_add_peers", "cm_dense_attn", "cm_dense_attn_strided",
            "cm_csp_mlp_mm1", "cm_csp_mlp_mm2", "cm_csp_scatter_add", "cm_mask_to_indices",
            "cm_bitmask_to_indices", "cm_select_columns", "cm_topk_indices", "cm_copy_indices", "cm_gather_rows", "cm_bitpack",
            "cm_bitunpack")

@@ -74,6 +74,8 @@ struct Params {
     int accumulate;
     int wide;                    // o (and cache) rows are 32-byte aligned: the epilogue moves full sectors per access
     int64_t mc_delta;            // != 0: o lives in a symmetric buffer; rows are stored to (o + mc_delta bytes), its NVLS multicast alias
+    int n_peers;                 // > 0: no multicast; rows are stored to (o + peer_delta[p] bytes) for every GPU p of the group (own copy included)
+    int64_t peer_delta[8];
     int stage;                   // 1: output (and cache) tiles go through shared memory and the TMA; 0: multicast epilogue (direct stores)
     int8_t pos[3][3];            // coordinate slots of (row, head, batch) in the q / cache / o tensor maps
     int num_tiles;
@@ -86,6 +88,13 @@ struct __align__(8) Barriers {
     uint64_t s_full[2], p_full[2], o_full[2];
     uint64_t c_full, st_full, st_free;       // cached tile landed | staging tile written by the epilogue | read out by the TMA store
 };
+
+// one 16-byte piece of an output row into every GPU's copy of the symmetric output buffer: one multimem.st through the
+// NVSwitch (NVLS), or one plain store per peer over NVLink when the group has no multicast object
+__device__ __forceinline__ void bcast_st_v4(const Params& P, char* local, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (P.mc_delta != 0) { multimem_st_v4(local + P.mc_delta, a, b, c, d); return; }
+    for (int p = 0; p < P.n_peers; p++) *reinterpret_cast<uint4*>(local + P.peer_delta[p]) = make_uint4(a, b, c, d);
+}
 
 __device__ __forceinline__ int tile_count(const Params& P, int tile) {
     int c = __ldg(P.counts + tile);
@@ -315,19 +324,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                 continue;
             }
             if (count <= 0) {
-                if (P.cache != nullptr) {
-                    if (row_ok) {
-                        const uint4* crow = reinterpret_cast<const uint4*>(P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)row * P.cs[2]);
+                // (gather-fused epilogue) no contribution: the cached row goes out as it is
+                if (row_ok) {
+                    const uint4* crow = reinterpret_cast<const uint4*>(P.cache + b * P.cs[0] + h * P.cs[1] + (int64_t)row * P.cs[2]);
 #pragma unroll
-                        for (int c = 0; c < 16; c++) {
-                            const uint4 t = __ldg(crow + c);
-                            if (P.mc_delta != 0) multimem_st_v4(reinterpret_cast<char*>(orow) + P.mc_delta + c * 16, t.x, t.y, t.z, t.w);
-                            else reinterpret_cast<uint4*>(orow)[c] = t;
-                        }
+                    for (int c = 0; c < 16; c++) {
+                        const uint4 t = __ldg(crow + c);
+                        bcast_st_v4(P, reinterpret_cast<char*>(orow) + c * 16, t.x, t.y, t.z, t.w);
                     }
-                } else if (!P.accumulate && row_ok) {
-#pragma unroll
-                    for (int c = 0; c < 16; c++) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0, 0, 0, 0);
                 }
                 continue;
             }
@@ -427,9 +431,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                             w[8 * c + j] = pack_bf16x2(bf16_lo(cv[c][j]) + bf16_lo(w[8 * c + j]), bf16_hi(cv[c][j]) + bf16_hi(w[8 * c + j]));
                     if (hf == 0) load_cache_half(1);
                 }
-                if (P.mc_delta != 0) {
-                    // Fused all-gather: the rows go to the NVLS multicast alias of the symmetric output buffer, and the
-                    // NVSwitch replicates them into every GPU while the other tiles are still being computed.  A
+                {
+                    // Fused all-gather: the rows go to the NVLS multicast alias of the symmetric output buffer -- the NVSwitch
+                    // replicates them into every GPU -- or, without multicast, to every peer's copy with plain stores over
+                    // NVLink, while the other tiles are still being computed.  A
                     // row-per-thread store pattern would put 16-byte packets on NVLink (packet-rate-bound: measured 1.7x
                     // SLOWER than a separate NCCL all-gather at 8 GPUs), so each group of 8 lanes first transposes its
                     // 8 rows x 8 pieces of 16 bytes with three butterfly shuffle stages: store j of a group then
@@ -451,26 +456,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                     }
                     // w[4j .. 4j+3] now holds piece t8 of the row owned by lane (lane & ~7) + j
                     const int row0 = row - t8;                      // first row of this 8-lane group
-                    char* gbase = reinterpret_cast<char*>(P.o + b * P.os[0] + h * P.os[1]) + P.mc_delta + hf * 128 + t8 * 16;
+                    char* gbase = reinterpret_cast<char*>(P.o + b * P.os[0] + h * P.os[1]) + hf * 128 + t8 * 16;
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         if (row0 + j < P.Nq)
-                            multimem_st_v4(gbase + (int64_t)(row0 + j) * P.os[2] * 2, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                } else if (row_ok) {
-                    if (!fused && P.accumulate) {
-                        // in-place delta add-back (csp_attn): o = bf16(o + delta) as 16-byte reductions at the L2 (the
-                        // reference uses a TMA reduce-add, csp_attn.cu:300)
-#pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            red_add_bf16x8(orow + hf * 64 + c * 8, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-                    } else if (P.wide) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) st_global_v8(orow + hf * 64 + c * 16, w + 8 * c);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            *reinterpret_cast<uint4*>(orow + hf * 64 + c * 8) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-                    }
+                            bcast_st_v4(P, gbase + (int64_t)(row0 + j) * P.os[2] * 2, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
                 }
             }
             tc_fence_before_sync();
@@ -564,7 +554,7 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
                          const int32_t* counts, int B, int H, int Nq, int Nk, const int64_t q_strides[3],
                          const int64_t k_strides[3], const int64_t v_strides[3], const int64_t c_strides[3],
                          const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, int accumulate, void* stream,
-                         int64_t mc_delta = 0) {
+                         int64_t mc_delta = 0, const int64_t* peer_delta = nullptr, int n_peers = 0) {
     if (B < 0 || H < 0 || Nq < 0 || Nk <= 0 || idx_row_stride <= 0) return CM_EINVAL;
     if (o_scale != 1 && o_scale != -1) return CM_EINVAL;
     if ((int64_t)B * H * Nq == 0) return CM_OK;
@@ -593,7 +583,10 @@ static int csp_attn_impl(const void* q, const void* k, const void* v, const void
     P.wide = wide_ok(o, o_strides) && (!cache || wide_ok(cache, c_strides)) ? 1 : 0;
     if (mc_delta != 0 && (!cache || (mc_delta & 15))) return CM_EINVAL;
     P.mc_delta = mc_delta;
-    P.stage = mc_delta == 0 ? 1 : 0;
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!cache || !peer_delta || mc_delta != 0))) return CM_EINVAL;
+    P.n_peers = n_peers;
+    for (int i = 0; i < n_peers; i++) { if (peer_delta[i] & 15) return CM_EINVAL; P.peer_delta[i] = peer_delta[i]; }
+    P.stage = (mc_delta == 0 && n_peers == 0) ? 1 : 0;
     int64_t tiles = (int64_t)B * H * P.G;
     if (tiles > 2147483647ll) return CM_EINVAL;
     P.num_tiles = (int)tiles;
@@ -617,6 +610,16 @@ extern "C" int cm_csp_attn_add_bcast(const void* q, const void* k, const void* v
     if (!cache || !cache_strides || multicast_delta_bytes == 0) return CM_EINVAL;
     return csp_attn_impl(q, k, v, cache, o_local, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides,
                          cache_strides, o_strides, idx_row_stride, o_scale, 0, stream, multicast_delta_bytes);
+}
+
+extern "C" int cm_csp_attn_add_peers(const void* q, const void* k, const void* v, const void* cache, void* o_local,
+                                     const int64_t* peer_delta_bytes, int n_peers, const int32_t* indices, const int32_t* counts,
+                                     int B, int H, int Nq, int Nk, const int64_t q_strides[3], const int64_t k_strides[3],
+                                     const int64_t v_strides[3], const int64_t cache_strides[3],
+                                     const int64_t o_strides[3], int64_t idx_row_stride, int o_scale, void* stream) {
+    if (!cache || !cache_strides || !peer_delta_bytes || n_peers <= 0) return CM_EINVAL;
+    return csp_attn_impl(q, k, v, cache, o_local, indices, counts, B, H, Nq, Nk, q_strides, k_strides, v_strides,
+                         cache_strides, o_strides, idx_row_stride, o_scale, 0, stream, 0, peer_delta_bytes, n_peers);
 }
 
 extern "C" int cm_csp_attn_add(const void* q, const void* k, const void* v, const void* cache, void* o,

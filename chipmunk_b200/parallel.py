@@ -68,7 +68,7 @@ class NvlsUnavailable(RuntimeError):
     """Symmetric memory / NVLS multicast cannot be used for this (group, shape) on this system."""
 
 
-def _symm_buffer(shape, dtype, device, group):
+def _symm_buffer(shape, dtype, device, group, need_multicast: bool = True):
     import torch.distributed._symmetric_memory as symm
 
     key = (tuple(shape), dtype, device.index, id(group))
@@ -78,21 +78,23 @@ def _symm_buffer(shape, dtype, device, group):
             hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
         except Exception as e:  # noqa: BLE001  (allocator / rendezvous failures are "not available", nothing else is)
             raise NvlsUnavailable(f"symmetric memory rendezvous failed: {e!r}") from e
-        if not getattr(hdl, "multicast_ptr", 0):
-            raise NvlsUnavailable("NVLS multicast is not available on this system: use sparse_attention_head_parallel(fused=False)")
         _SYMM[key] = (buf, hdl)
-    return _SYMM[key]
+    buf, hdl = _SYMM[key]
+    if need_multicast and not getattr(hdl, "multicast_ptr", 0):
+        raise NvlsUnavailable("NVLS multicast is not available on this system: use fused='peers' or fused=False")
+    return buf, hdl
 
 
-def fused_gather_available(shape, dtype, device, group=None) -> bool:
-    """Whether EVERY rank of `group` can use the multicast-fused gather for this output shape.  The probe (symmetric
-    allocation + rendezvous + multicast pointer) runs once per (group, shape); the ranks then agree on the outcome
-    with an all_reduce(MIN), so that no rank can enter the device barriers of the fused path while another one falls
-    back to the NCCL all-gather (mismatched collectives = hang).  The decision is cached."""
-    key = (id(group), tuple(shape), dtype, device.index)
+def fused_gather_available(shape, dtype, device, group=None, mode: str = "multicast") -> bool:
+    """Whether EVERY rank of `group` can use the fused gather for this output shape: mode "multicast" = NVLS multicast
+    stores, mode "peers" = plain stores into every peer's copy (symmetric memory without a multicast object).  The probe
+    (symmetric allocation + rendezvous [+ multicast pointer]) runs once per (group, shape, mode); the ranks then agree on
+    the outcome with an all_reduce(MIN), so that no rank can enter the device barriers of the fused path while another
+    one falls back to the NCCL all-gather (mismatched collectives = hang).  The decision is cached."""
+    key = (id(group), tuple(shape), dtype, device.index, mode)
     if key not in _FUSED_OK:
         try:
-            _symm_buffer(shape, dtype, device, group)
+            _symm_buffer(shape, dtype, device, group, need_multicast=(mode == "multicast"))
             ok = torch.ones(1, device=device, dtype=torch.int32)
         except NvlsUnavailable:
             ok = torch.zeros(1, device=device, dtype=torch.int32)
@@ -101,9 +103,10 @@ def fused_gather_available(shape, dtype, device, group=None) -> bool:
     return _FUSED_OK[key]
 
 
-def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads: int, group=None) -> torch.Tensor:
+def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads: int, group=None, mode: str = "multicast") -> torch.Tensor:
     """One sparse attention step, heads sharded over the ranks of `group` (num_heads % world == 0), with the
-    all-gather of O fused into the kernel's epilogue (NVLS multicast stores).  Returns the full [B, H, N, D]
+    all-gather of O fused into the kernel's epilogue: NVLS multicast stores (mode "multicast"), or plain stores into every
+    peer's copy over NVLink (mode "peers": no multicast object needed).  Returns the full [B, H, N, D]
     output as a view of the symmetric buffer: it stays valid until the next call with the same shape."""
     from . import torch_ops as _t
 
@@ -111,8 +114,14 @@ def sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_
     B, h_local, N, D = q.shape
     if num_heads != h_local * world:
         raise RuntimeError("fused head-parallel attention needs num_heads == world_size * local heads")
-    buf, hdl = _symm_buffer((world, B, h_local, N, D), q.dtype, q.device, group)
+    buf, hdl = _symm_buffer((world, B, h_local, N, D), q.dtype, q.device, group, need_multicast=(mode == "multicast"))
     hdl.barrier(channel=0)                       # every rank has consumed the previous contents of the buffer
+    if mode == "peers":
+        mine = int(hdl.buffer_ptrs[rank])
+        deltas = [int(hdl.buffer_ptrs[r]) - mine for r in range(world)]
+        _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1, out=buf[rank], peer_deltas=deltas)
+        hdl.barrier(channel=1)
+        return buf.permute(1, 0, 2, 3, 4).reshape(B, num_heads, N, D)
     mc_delta = int(hdl.multicast_ptr) - int(hdl.buffer_ptrs[rank])
     _t.csp_attn_add(q, k, v, o_cache, indices, counts, 1, out=buf[rank], multicast_delta=mc_delta)
     hdl.barrier(channel=1)                       # every rank's kernel has finished: all slices are everywhere
@@ -123,7 +132,8 @@ def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads:
     """One sparse attention step with heads sharded over the ranks of `group`.
     q/k/v/o_cache/indices/counts hold this rank's heads only; returns the full [B, H, N, D] output.
     fused=None: use the multicast-fused kernel when NVLS symmetric memory is available (8 GPUs, 720p layer:
-    1.75 ms vs 2.74 ms), else the in-place NCCL all-gather; fused=False forces the NCCL path."""
+    1.83 ms vs 2.80 ms), else the peer-store fused kernel when symmetric memory is available without multicast, else the
+    in-place NCCL all-gather; fused=False forces the NCCL path, fused="peers" the peer-store kernel."""
     from . import torch_ops as _t
 
     if fused is not False and dist.is_initialized() and dist.get_world_size(group) > 1 \
@@ -131,10 +141,13 @@ def sparse_attention_head_parallel(q, k, v, o_cache, indices, counts, num_heads:
         w = dist.get_world_size(group)
         B_, hl_, N_, D_ = q.shape
         # decided once per (group, shape) by ALL ranks together; kernel / argument errors of the fused call propagate
-        if fused_gather_available((w, B_, hl_, N_, D_), q.dtype, q.device, group):
+        shape = (w, B_, hl_, N_, D_)
+        if fused != "peers" and fused_gather_available(shape, q.dtype, q.device, group):
             return sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads, group)
+        if w <= 8 and fused_gather_available(shape, q.dtype, q.device, group, mode="peers"):
+            return sparse_attention_head_parallel_fused(q, k, v, o_cache, indices, counts, num_heads, group, mode="peers")
         if fused:
-            raise NvlsUnavailable("fused=True but symmetric memory / NVLS multicast is not available on every rank")
+            raise NvlsUnavailable("a fused gather was requested but symmetric memory is not available on every rank")
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     B, h_local, N, D = q.shape

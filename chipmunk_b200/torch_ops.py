@@ -87,7 +87,7 @@ def csp_attn(q, k, v, o, indices, indices_counts, o_scale):
     _launch_csp_attn(q, k, v, o, indices, indices_counts, o_scale, 1)
 
 
-def csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale: int = 1, out=None, multicast_delta: int = 0):
+def csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale: int = 1, out=None, multicast_delta: int = 0, peer_deltas=None):
     """o = bf16(cache + o_scale * delta) as a fresh tensor, or into `out` (any [B,H,N,128] bf16 view with
     16-byte-aligned strides, e.g. this rank's slice of an all-gather buffer).  B200 addition: the sparse
     step's `o = cache.clone(); csp_attn(..., o, ...)` in one pass; `cache` is left untouched."""
@@ -107,7 +107,15 @@ def csp_attn_add(q, k, v, cache, indices, indices_counts, o_scale: int = 1, out=
     if B * H * Nq == 0:
         return o
     with torch.cuda.device(q.device):
-        if multicast_delta:
+        if peer_deltas is not None:
+            # `out` is this rank's slice of a symmetric buffer; rows are stored into every peer's copy over NVLink (parallel.py)
+            _chk(out is not None and not multicast_delta, "peer_deltas needs out= (a slice of a symmetric-memory buffer) and no multicast_delta")
+            arr = (C.c_int64 * len(peer_deltas))(*[int(d) for d in peer_deltas])
+            check(lib.cm_csp_attn_add_peers(_ptr(q), _ptr(k), _ptr(v), _ptr(cache), _ptr(o), arr, len(peer_deltas),
+                                            _ptr(indices), _ptr(indices_counts), B, H, Nq, Nk, strides3(q), strides3(k),
+                                            strides3(v), strides3(cache), strides3(o), indices.shape[3], int(o_scale),
+                                            stream_ptr(q.device)), "csp_attn_add_peers")
+        elif multicast_delta:
             # `out` is this rank's slice of a symmetric buffer; rows go to its NVLS multicast alias (parallel.py)
             _chk(out is not None, "multicast_delta needs out= (a slice of a symmetric-memory buffer)")
             check(lib.cm_csp_attn_add_bcast(_ptr(q), _ptr(k), _ptr(v), _ptr(cache), _ptr(o), int(multicast_delta),

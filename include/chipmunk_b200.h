@@ -87,6 +87,18 @@ int cm_csp_attn_add_bcast(const void* q, const void* k, const void* v, const voi
                           const int64_t v_strides[3], const int64_t cache_strides[3], const int64_t o_strides[3],
                           int64_t idx_row_stride, int o_scale, void* stream);
 
+/* The same fused gather for an NVLink domain WITHOUT a multicast object (or when NVLS is disabled): every output row is
+ * stored with plain 16-byte stores into each peer's copy of the symmetric buffer, `peer_delta_bytes[p]` = (address of GPU
+ * p's buffer in this process' address space) - (address of the local buffer), own copy included (delta 0), n_peers <= 8.
+ * n_peers x the store traffic of the multicast variant on this GPU's NVLink egress, still hidden behind the remaining tiles. */
+int cm_csp_attn_add_peers(const void* q, const void* k, const void* v, const void* cache, void* o_local,
+                          const int64_t* peer_delta_bytes, int n_peers,
+                          const int32_t* indices, const int32_t* counts,
+                          int B, int H, int Nq, int Nk,
+                          const int64_t q_strides[3], const int64_t k_strides[3],
+                          const int64_t v_strides[3], const int64_t cache_strides[3], const int64_t o_strides[3],
+                          int64_t idx_row_stride, int o_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Dense attention with the statistics the sparse steps need.
  * Replaces chipmunk::dense_attn        (csrc/attn/dense_attn.cu:246-371, schema chipmunk.cpp:54)
