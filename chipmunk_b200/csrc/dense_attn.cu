@@ -58,6 +58,31 @@ constexpr int WARP_DRAIN0 = 8, WARP_MMA = 12, WARP_TMA = 13;
 constexpr int REG_SOFTMAX = 192, REG_OTHER = 64;    // setmaxnreg budgets: 256 x 192 + 256 x 64 = 64 K registers
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_CS = 384;
 
+#ifndef CM_DENSE_POLY
+#define CM_DENSE_POLY 4       // every CM_DENSE_POLY-th pair of scores is exponentiated on the FMA pipe (0: all on the MUFU)
+#endif
+// exp2 of two fp32 on the FMA / ALU pipes: x = n + f (round to nearest with the 1.5*2^23 trick), 2^f by a degree-3
+// Chebyshev fit on [-0.5, 0.5] (relative error 1.0e-4, far below the bf16 rounding of P), 2^n added into the exponent
+// field.  The two softmax warps of an SM sub-partition exponentiate at the same time (they meet on the pair barrier every
+// step), so the 4-lane MUFU is contended during that phase while the FMA pipe idles: moving a share of the exponentials
+// there shortens the phase.  (In the column-sparse kernel, one warp per sub-partition, the same trick gains nothing.)
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x) {
+    float x0, x1;
+    unpack_f32x2(x, x0, x1);
+    const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t t = fadd2(xc, pack_f32x2(12582912.f, 12582912.f));
+    const uint64_t n = fadd2(t, pack_f32x2(-12582912.f, -12582912.f));
+    const uint64_t f = ffma2(n, pack_f32x2(-1.f, -1.f), xc);
+    uint64_t p = ffma2(f, pack_f32x2(0.0559220356f, 0.0559220356f), pack_f32x2(0.2426400828f, 0.2426400828f));
+    p = ffma2(p, f, pack_f32x2(0.6931210340f, 0.6931210340f));
+    p = ffma2(p, f, pack_f32x2(0.9999244815f, 0.9999244815f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(p, q0, q1);
+    return pack_f32x2(__uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23)),
+                      __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23)));
+}
+
 struct Params {
     float* l;                  // [B,H,Nq] or null
     const float* p;            // [B,H,Nq] previous step's l (column sums only)
@@ -378,7 +403,9 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                         const uint64_t x = ffma2(pack_f32x2(__uint_as_float(s[c0 + j]), __uint_as_float(s[c0 + j + 1])), c2, nm2);
                         float x0, x1;
                         unpack_f32x2(x, x0, x1);
-                        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                        float p0, p1;
+                        if (CM_DENSE_POLY > 0 && ((j >> 1) % (CM_DENSE_POLY > 0 ? CM_DENSE_POLY : 1)) == 0) unpack_f32x2(exp2_poly2(x), p0, p1);
+                        else { p0 = fast_exp2(x0); p1 = fast_exp2(x1); }
                         acc[(j >> 1) & 1] = fadd2(acc[(j >> 1) & 1], pack_f32x2(p0, p1));
                         pk[j >> 1] = pack_bf16x2(p0, p1);
                     }

@@ -169,15 +169,16 @@ __device__ __forceinline__ void emit_row(const uint32_t* words, uint32_t* tw, in
     int32_t* dest = staged ? stage : out;
     // ---- emit set columns
     int pos = sc.warp_tot[warp] + incl - cnt;
+    int c = w0 / WJ, j = w0 - c * WJ;             // class and word group of transposed word w0 (one division per thread)
     for (int i = w0; i < w1; i++) {
         uint32_t t = tw[i];
-        const int c = i / WJ, j = i - c * WJ;
         const int col0 = 1024 * j + c;            // column of bit b: 32 (32 j + b) + c
         while (t) {
             const int bbit = __ffs(t) - 1;
             t &= t - 1;
             dest[pos++] = col0 + 32 * bbit;
         }
+        if (++j == WJ) { j = 0; c++; }
     }
     // ---- pad with the first unset columns (ascending), write the count
     if (warp == 0) {

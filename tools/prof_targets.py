@@ -29,6 +29,11 @@ def run(what):
         q, k, v = (torch.randn(1, H, N, 128, device=dev, generator=g).to(BF) for _ in range(3))
         p = torch.rand(1, H, N, 1, device=dev, generator=g) * 1e-3 + 1e-5
         T._launch_dense(q, k, v, p if what == "dense_cs" else None)
+    elif what in ("dense_c3", "dense_cs_c3"):
+        H, N = 24, 119056
+        q, k, v = (torch.randn(1, H, N, 128, device=dev, generator=g).to(BF) for _ in range(3))
+        p = torch.rand(1, H, N, 1, device=dev, generator=g) * 1e-3 + 1e-5
+        T._launch_dense(q, k, v, p if what == "dense_cs_c3" else None)
     elif what == "c3attn":
         from bench import make_packed_mask, C3_N, C3_COUNT
         n, G = C3_N, (C3_N + 191) // 192
