@@ -109,8 +109,10 @@ class SparseDiffAttn(nn.Module):
             # tk == 0: static mask only (the group flags are ignored, reference :135)
             static = singleton_static_words
             flags = singleton_group_flags if tk > 0 else None
-            packed, shape, inds, counts = ops.select_columns(
-                cs, tk, multiple_of, 0.01 if tk > 0 else 0.0, static, flags, None, bm)
+            # the reference hard-codes 1 % random columns (randint(0, 100) == 0, :77); `attn.random_columns` overrides
+            # the share (0 disables it: the golden-vector tests need both sides to select the same columns)
+            rand = float(cfg.get("random_columns", 0.01)) if tk > 0 else 0.0
+            packed, shape, inds, counts = ops.select_columns(cs, tk, multiple_of, rand, static, flags, None, bm)
             self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
             self.storage.set_indices(packed)
             return inds, counts
