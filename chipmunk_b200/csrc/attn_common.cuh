@@ -21,7 +21,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;                        // in log2 unit
 // (reference csp_attn.cu:272) by loading them as -inf.
 template <bool TAIL>
 __device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref,
-                                             float& l_sum, uint64_t* pv_done = nullptr, uint32_t pv_parity = 0) {
+                                             float& l_sum, bool active = true) {
     uint32_t s[KT];
 #pragma unroll
     for (int c = 0; c < KT; c += 32) tmem_ld32(tS + c, s + c);
@@ -42,7 +42,10 @@ __device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid
     }
     const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
     // ---- lazy rescale of the running state (always taken on the first step: m_ref = -inf)
-    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
+    // Lanes that own no row -- lanes 16-31 of a block-1 warp (M = 64 accumulator, csp_attn.cu) -- run the same instruction
+    // stream on whatever their TMEM lanes hold, but never vote.  (Branching them off the arithmetic was measured: the
+    // divergence costs 8 % of the kernel, far more than the idle lanes' power.)
+    const bool need = active && (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
     if (__any_sync(0xffffffffu, need)) {
         float alpha = 1.f;
         if (need) {
@@ -51,8 +54,6 @@ __device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid
             l_sum *= alpha;
         }
         if (kk > 0) {
-            // O may only be touched once the previous step's P.V has landed (2-CTA kernel: S runs ahead of P.V)
-            if (pv_done) { mbar_wait(pv_done, pv_parity); tc_fence_after_sync(); }
 #pragma unroll 1
             for (int c0 = 0; c0 < D; c0 += 32) {
                 uint32_t r[32];
@@ -93,7 +94,8 @@ __device__ __forceinline__ void softmax_step(uint32_t tS, uint32_t tO, int valid
 // A step with at most 32 valid key columns (the 16-column tail that a count = k*112 or k*128+16 list ends with):
 // one 32-column chunk instead of four.  The step sits on the tile's critical chain like every other one, and at
 // FLUX sizes (7 steps per tile) a full-width pass over a 16-column tail is ~4 % of the kernel.
-__device__ __forceinline__ void softmax_step_narrow(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref, float& l_sum) {
+__device__ __forceinline__ void softmax_step_narrow(uint32_t tS, uint32_t tO, int valid, int kk, float& m_ref, float& l_sum,
+                                                    bool active = true) {
     uint32_t s[32];
     tmem_ld32(tS, s);
     tmem_ld_wait();
@@ -103,7 +105,7 @@ __device__ __forceinline__ void softmax_step_narrow(uint32_t tS, uint32_t tO, in
 #pragma unroll
     for (int j = 1; j < 31; j += 2) mx = fmax3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
     const float m_tile = fmaxf(mx, __uint_as_float(s[31]));
-    const bool need = (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
+    const bool need = active && (m_tile - m_ref) * SCALE_LOG2 > RESCALE_THRESHOLD;
     if (__any_sync(0xffffffffu, need)) {
         float alpha = 1.f;
         if (need) {

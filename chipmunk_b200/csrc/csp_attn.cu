@@ -12,8 +12,13 @@
 //     MMA warp (1 thread)  S = Q K^T   (tcgen05.mma SS, M=128 N<=128 K=128, fp32 in TMEM), twice:
 //                          query rows 0-127 ("block 0") and 128-191 ("block 1"),
 //                          O += P V    (tcgen05.mma TS: P read from TMEM, V as MN-major smem),
-//     softmax warps (4+2)  one thread per query row: TMEM -> regs, running max with lazy
-//                          rescale, exp2, row sum, P (bf16) written back over S in TMEM,
+//     softmax warps (4+4)  one thread per query row: TMEM -> regs, running max with lazy
+//                          rescale, exp2, row sum, P (bf16) written back over S in TMEM.  Block 1 is an M = 64
+//                          accumulator (row m on TMEM lane (m % 16) + 32 (m / 16)): 16 rows per lane quadrant, so
+//                          its four warps use lanes 0-15 each.  An M = 64 MMA takes as many cycles as an M = 128 one
+//                          but far less power (tests/probes/probe_mma_power.cu: under the 1 kW cap a pure MMA stream
+//                          clocks 1.81 GHz at M = 64, 1.57 GHz at M = 128 with 64 zero rows), and the kernel runs at the
+//                          cap: -3.3 % at the 720p shape against an M = 128 block 1 with two softmax warps,
 //     epilogue             (same threads) O / l * o_scale -> bf16 (+ the cached tile, read from shared memory) into a
 //                          128B-swizzled staging tile that the TMA thread stores (csp_128_attn, csp_attn_add) or
 //                          reduce-adds at the L2 (csp_attn, like the reference's TMA store_add, csp_attn.cu:300).
@@ -34,26 +39,36 @@
 #include "attn_common.cuh"
 #include "tma.cuh"
 
+#ifndef CM_ATTN_REG_SOFTMAX
+#define CM_ATTN_REG_SOFTMAX 208
+#define CM_ATTN_REG_MMA 32
+#define CM_ATTN_REG_PROD 64
+#endif
+
 namespace cm {
 namespace attn {
 
 constexpr int NSLOT = 4;            // 32 KB K/V slots
 constexpr int SLOT_BYTES = KT * D * 2;
-// Geometry: the reference's 192-query index groups = one full M=128 block + one half-empty one (an M=128 MMA for 64 rows).
+// Geometry: the reference's 192-query index groups = one M=128 block + one M=64 block.
 struct GEO {
     static constexpr int QROWS = QG;                             // query rows per tile
     static constexpr int Q_HALF_BYTES = QROWS * 128;             // one 64-wide d-half of the Q tile
     static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB
     static constexpr int STAGE_BYTES = Q_BYTES;                  // 48 KB: the cached output tile in, the output tile out (TMA both ways)
     static constexpr int SMEM_BYTES = Q_BYTES + STAGE_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
-    // warps 0-3 softmax blk0 | 4-5 softmax blk1, 6 MMA, 7 TMA (Q tile, cached tile, output tile) | 8-11 K/V gather producers
-    static constexpr int NUM_THREADS = 384;
-    static constexpr int WARP_MMA = 6;
-    static constexpr int NUM_SOFTMAX_WARPS = 6;
-    static constexpr int REG_SOFTMAX = 208;                      // setmaxnreg budgets: 64 K registers per SM
-    static constexpr int REG_OTHER = 80;
+    // warps 0-3 softmax blk0 | 4-7 softmax blk1 (16 rows each) | 8 MMA, 9 TMA (Q tile, cached tile, output tile), 10-11 idle |
+    // 12-15 K/V gather producers
+    static constexpr int NUM_THREADS = 512;
+    static constexpr int WARP_MMA = 8;
+    static constexpr int WARP_TMA = 9;
+    static constexpr int NUM_SOFTMAX_WARPS = 8;
+    static constexpr int REG_SOFTMAX = CM_ATTN_REG_SOFTMAX;      // setmaxnreg budgets per warpgroup: 64 K registers per SM
+    static constexpr int REG_MMA = CM_ATTN_REG_MMA;
+    static constexpr int REG_OTHER = CM_ATTN_REG_PROD;
 };
-constexpr int WARP_PROD0 = 8;
+constexpr int WARP_PROD0 = 12;
+constexpr int INACTIVE_ROW = 1 << 28;          // r_in_tile of the lanes 16-31 of a block-1 softmax warp: beyond every Nq
 constexpr int NUM_PROD = 128;
 
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 384;
@@ -195,9 +210,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
-        setmaxnreg_inc<GEO::REG_SOFTMAX>();   // warpgroup-wide: the MMA warp shares warpgroup 1 with softmax warps
+        setmaxnreg_dec<GEO::REG_MMA>();
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
-        const uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
+        const uint32_t idesc_pv0 = umma_idesc_bf16(128, D, 0, 1), idesc_pv1 = umma_idesc_bf16(64, D, 0, 1);
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
         const uint64_t desc_k = umma_smem_desc(sKV, 16, 1024);                   // K-major B: gathered K rows
         const uint64_t desc_v = umma_smem_desc(sKV, SLOT_BYTES / 2, 1024);       // MN-major B: gathered V rows
@@ -213,7 +228,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
             // The issuing thread is the kernel's scarcest resource: descriptors are built once (their fields
             // are constant but for the 14-bit start address) and each MMA only adds a compile-time offset.
             auto issue_S = [&](int blk, uint32_t slot, int cols) {
-                const uint32_t idesc = umma_idesc_bf16(128, cols, 0, 0);
+                const uint32_t idesc = umma_idesc_bf16(blk ? 64 : 128, cols, 0, 0);
                 const uint32_t d = tm + (blk ? TM_S1 : TM_S0);
                 const uint64_t ad0 = desc_q + (uint64_t)(blk * ((128 * 128) >> 4));
                 const uint64_t bd0 = desc_k + (uint64_t)(slot * (SLOT_BYTES >> 4));
@@ -229,6 +244,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                 const uint32_t d = tm + (blk ? TM_O1 : TM_O0);
                 const uint32_t a = tm + (blk ? TM_S1 : TM_S0);
                 const uint64_t bd0 = desc_v + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                const uint32_t idesc_pv = blk ? idesc_pv1 : idesc_pv0;
                 if (CM_DBG(P, 2)) return;
                 if (cols == KT) {
 #pragma unroll
@@ -290,15 +306,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     // =========================================================================== softmax + epilogue
     else if (warp < GEO::NUM_SOFTMAX_WARPS) {
         setmaxnreg_inc<GEO::REG_SOFTMAX>();
-        const int blk = warp >> 2;                         // 0: rows 0-127, 1: rows 128-191
-        const int r_in_tile = blk * 128 + (warp & 3) * 32 + lane;
+        const int blk = warp >> 2;                         // 0: rows 0-127 (M = 128), 1: rows 128-191 (M = 64)
+        // block 1: row m of the M = 64 accumulator sits on TMEM lane (m % 16) + 32 (m / 16): lanes 0-15 of every quadrant;
+        // lanes 16-31 of its warps only take part in the warp-wide TMEM instructions
+        const bool active = blk == 0 || lane < 16;
+        const int r_in_tile = blk == 0 ? (warp & 3) * 32 + lane : (active ? 128 + (warp & 3) * 16 + lane : INACTIVE_ROW);
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tm + (blk ? TM_S1 : TM_S0) + lane_off;
         const uint32_t tO = tm + (blk ? TM_O1 : TM_O0) + lane_off;
         uint32_t sc = 0, oc = 0;
         uint32_t ti = 0;                                   // tiles of this CTA so far (phases of c_full / st_full / st_free)
         const uint32_t sw = (uint32_t)(r_in_tile & 7);
-        const uint32_t srow = sStage + (uint32_t)r_in_tile * 128;     // this row in a d-half of the staging tile (halves 24 KB apart)
+        const uint32_t srow = sStage + (uint32_t)(active ? r_in_tile : 0) * 128;     // this row in a d-half of the staging tile (halves 24 KB apart)
         // the staging tile becomes writable: the cached tile has landed in it (fused add-back), or the previous tile's
         // store has read it out
         auto stage_ready = [&]() {
@@ -315,12 +334,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
             if (count <= 0 && P.stage) {
                 // no contribution: the cached tile passes through as it is; a fresh output (or a delta to add) is zero
                 stage_ready();
-                if (P.cache == nullptr) {
+                if (P.cache == nullptr && active) {
 #pragma unroll
                     for (int c = 0; c < 16; c++) st_shared_v4(srow + (c >> 3) * (GEO::STAGE_BYTES / 2) + ((((uint32_t)c & 7) ^ sw) << 4), 0, 0, 0, 0);
                     fence_proxy_async_smem();
                 }
-                mbar_arrive(&bar.st_full);
+                if (active) mbar_arrive(&bar.st_full);
                 continue;
             }
             if (count <= 0) {
@@ -344,12 +363,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                 mbar_wait(&bar.s_full[blk], sc & 1); sc++;
                 tc_fence_after_sync();
                 if (CM_DBG(P, 4)) { l_sum = 1.f; }
-                else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum);
-                else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum);
-                else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum);
+                else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum, active);
+                else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum, active);
+                else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum, active);
                 tmem_st_wait();
                 tc_fence_before_sync();
-                mbar_arrive(&bar.p_full[blk]);
+                if (active) mbar_arrive(&bar.p_full[blk]);
             }
             // ---- epilogue: O / l * scale (+ cached o) -> bf16
             if (P.stage) {
@@ -375,6 +394,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                         for (int j = 0; j < 4; j++)
                             w[j] = pack_bf16x2(__uint_as_float(r[8 * c + 2 * j]) * inv, __uint_as_float(r[8 * c + 2 * j + 1]) * inv);
                         const uint32_t a = base + (((uint32_t)c ^ sw) << 4);
+                        if (!active) continue;
                         if (fused) {
                             // o = bf16(cache + bf16(delta))
                             const uint4 cv = ld_shared_v4(a);
@@ -388,7 +408,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                 }
                 fence_proxy_async_smem();
                 tc_fence_before_sync();
-                mbar_arrive(&bar.st_full);
+                if (active) mbar_arrive(&bar.st_full);
                 continue;
             }
             // multicast epilogue (cm_csp_attn_add_bcast): direct stores to the NVLS alias of the symmetric output buffer
@@ -467,9 +487,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
         }
     }
     else {
-        // =========================================================================== TMA thread (warp 7)
-        setmaxnreg_inc<GEO::REG_SOFTMAX>();        // warpgroup-wide: warp 7 sits in the softmax group
-        if (lane == 0) {
+        // =========================================================================== TMA thread (warp 9); warps 10-11 idle
+        setmaxnreg_dec<GEO::REG_MMA>();            // warpgroup-wide: warps 8-11
+        if (warp == GEO::WARP_TMA && lane == 0) {
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_o);
             uint32_t qn = 0;                        // Q tiles loaded so far
             int tq = blockIdx.x;                    // first tile whose Q has not been requested yet
