@@ -286,7 +286,8 @@ def run_ours(args):
     roofline = _roof(attn_alg_bytes(hl, n, count), t_attn, hbm_gbs, peak_src, traffic_db.get("c3_csp_attn_add") if world == 1 else None)
     roofline.update({"note": "SURVEY 8d gather roofline: algorithmic indexed-KV bytes / HBM peak.  `traffic` (ncu DRAM bytes per launch) is ~7x "
                              "smaller: a head's K/V (61 MB) stays in the 126 MB L2 under head-major tile order, so the gather is served by L2 "
-                             "and the kernel is bound by its S -> softmax -> P.V chain (tensor pipe 63 % active), not by HBM",
+                             "and the kernel is bound by its S -> softmax -> P.V chain (tensor pipe 63 % active) and by the 1 kW power "
+                             "cap (it runs at ~1.6 of 1.965 GHz: profiles/r02_probe_mma_power.txt), not by HBM",
                      "kernel": "attn::attn_kernel<false> (csp_attn_add)" + (" + fused multicast gather of O" if use_fused else (" + ncclAllGather" if world > 1 else "")),
                      "launch_us": round(t_attn * 1e3, 1), "algorithmic_bytes_per_launch": attn_alg_bytes(hl, n, count),
                      "tensor_tflops": round(4.0 * QG * count * D * hl * G / (t_attn * 1e-3) / 1e12, 1),
@@ -295,6 +296,11 @@ def run_ours(args):
     kernels = {"bitmask_to_indices": {"us": round(t_m2i * 1e3, 1), "algorithmic_MB": round(m2i_bytes / 1e6, 1),
                                       "GB/s": round(m2i_bytes / t_m2i / 1e6, 1), "frac_of_hbm_peak": round(m2i_bytes / t_m2i / 1e6 / hbm_gbs, 4)},
                "csp_attn_add": {"us": round(t_attn * 1e3, 1), "gather_roofline_frac": roofline["frac"]}}
+    # B200 option `attn.keep_indices_resident` (off by default = the reference's behaviour): the index lists of the last full
+    # step stay in HBM (0.5 GB per layer at 720p), a sparse step is the attention launch alone.  Reported beside the headline.
+    resident = {"ms_per_step": round(t_attn, 4), "value": round(C3_DENSE_FLOPS / (t_attn * 1e-3) / 1e12, 2), "unit": "TFLOP/s-equiv",
+                "index_bytes_per_layer": int(hl * G * (n + 1) * 4),
+                "note": "attn.keep_indices_resident: index lists kept in HBM between steps instead of re-derived from the bit mask"}
 
     # ---- e2e: the same step from pinned HOST buffers (q, k, v up; this rank's o down), H2D | compute | D2H streams
     numa = bind_to_gpu_numa_node(local)
@@ -402,7 +408,7 @@ def run_ours(args):
                        "l2": "per-step working set (q,k,v,o,cache 3.7 GB + 7.1 GB of indices) >> 126 MB L2: every step streams from HBM"},
             "roofline": roofline, "cpu_baseline": extras.pop("cpu_baseline", None), "e2e": e2e, "gpu_launches": 2 * steps,
             "clocks": clocks, "us_per_layer": {"bitmask_to_indices": round(t_m2i * 1e3, 1), "attn": round(t_attn * 1e3, 1)},
-            "kernels": kernels,
+            "kernels": kernels, "sparse_step_indices_resident": resident,
         }
         line.update(extras)
         print(json.dumps(line))

@@ -37,6 +37,9 @@ class SparseDiffAttn(nn.Module):
         self.layer_counter = layer_counter
         self.storage = AttnStorage(layer_num, init_names=["indices", "out_cache"])
         self.mask_shape = [None] * GLOBAL_CONFIG["num_model_invocations_per_inference_step"]
+        # `attn.keep_indices_resident`: (indices, counts) of the last selection per model invocation, kept in HBM so that
+        # sparse steps skip the bit mask -> indices kernel (see _stored_indices)
+        self._resident = {}
 
     # ------------------------------------------------------------------ static (local) mask
     def initialize_static_mask(self, seq_shape: Tuple, txt_len: int, local_heads_num: int, device):
@@ -83,10 +86,21 @@ class SparseDiffAttn(nn.Module):
 
     # ------------------------------------------------------------------ index bookkeeping
     def _stored_indices(self, multiple_of: int, bm: int):
+        """Index lists of the current selection.  With compressed indices the reference keeps only the bit-packed mask
+        and re-derives the lists on EVERY sparse step (bitunpack + mask_to_indices, modules/attn.py:173-176): 80 GB of
+        HBM cannot hold 0.5 GB of lists per layer at 720p.  180 GB can: `attn.keep_indices_resident: true` (default
+        off = the reference's behaviour) keeps the lists of the last full step in HBM -- 60 layers x 0.5 GB = 30 GB at
+        720p -- and a sparse step is the attention kernel alone (-4.5 % of the step)."""
         cfg = GLOBAL_CONFIG["attn"]
         if cfg["should_compress_indices"]:
-            shape = self.mask_shape[self.layer_counter.cur_model_invocation_per_step]
-            return ops.bitmask_to_indices(self.storage.get_indices(), shape, multiple_of, bm)
+            inv = self.layer_counter.cur_model_invocation_per_step
+            keep = bool(cfg.get("keep_indices_resident", False))
+            if keep and inv in self._resident:
+                return self._resident[inv]
+            out = ops.bitmask_to_indices(self.storage.get_indices(), self.mask_shape[inv], multiple_of, bm)
+            if keep:
+                self._resident[inv] = out
+            return out
         return self.storage.get_indices(), self.storage.get_counts()
 
     def _select_indices(self, cs: Tensor, q: Tensor, k: Tensor, multiple_of: int, bm: int):
@@ -103,9 +117,14 @@ class SparseDiffAttn(nn.Module):
                 else:
                     mask = singleton_static_mask[..., : cs.shape[-2], : cs.shape[-1]]
                 packed, shape = ops.bitpack(mask)
-                self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
+                inv = self.layer_counter.cur_model_invocation_per_step
+                self.mask_shape[inv] = shape
                 self.storage.set_indices(packed)
-                return ops.mask_to_indices(mask, multiple_of, bm)
+                out = ops.mask_to_indices(mask, multiple_of, bm)
+                self._resident.pop(inv, None)
+                if cfg.get("keep_indices_resident", False):
+                    self._resident[inv] = out
+                return out
             # tk == 0: static mask only (the group flags are ignored, reference :135)
             static = singleton_static_words
             flags = singleton_group_flags if tk > 0 else None
@@ -113,8 +132,12 @@ class SparseDiffAttn(nn.Module):
             # the share (0 disables it: the golden-vector tests need both sides to select the same columns)
             rand = float(cfg.get("random_columns", 0.01)) if tk > 0 else 0.0
             packed, shape, inds, counts = ops.select_columns(cs, tk, multiple_of, rand, static, flags, None, bm)
-            self.mask_shape[self.layer_counter.cur_model_invocation_per_step] = shape
+            inv = self.layer_counter.cur_model_invocation_per_step
+            self.mask_shape[inv] = shape
             self.storage.set_indices(packed)
+            self._resident.pop(inv, None)
+            if cfg.get("keep_indices_resident", False):
+                self._resident[inv] = (inds, counts)
             return inds, counts
         groups = (q.shape[-2] + bm - 1) // bm
         cs = cs[..., : (kseq + bm - 1) // bm, :kseq]

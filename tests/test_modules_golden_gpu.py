@@ -39,8 +39,9 @@ def _close(got: torch.Tensor, want: torch.Tensor, rel: float, scale: torch.Tenso
     assert float(err) <= rel, f"{what}: relative error {float(err):.3e} > {rel:.1e}"
 
 
-@pytest.mark.parametrize("name,torch_selection", [("hunyuan", False), ("hunyuan", True), ("flux", False), ("flux", True)])
-def test_sparse_diff_attn_matches_reference_modules(cm, cuda, monkeypatch, name, torch_selection):
+@pytest.mark.parametrize("name,torch_selection,resident", [("hunyuan", False, False), ("hunyuan", True, False), ("hunyuan", False, True),
+                                                          ("hunyuan", True, True), ("flux", False, False), ("flux", True, False)])
+def test_sparse_diff_attn_matches_reference_modules(cm, cuda, monkeypatch, name, torch_selection, resident):
     z = np.load(os.path.join(GOLD, "modules_attn.npz"))
     compressed, pad, multiple_of, tt, th, tw, txt_len, tk, local_voxels, H, salt = (int(x) for x in z[f"{name}_cfg"])
     N = tt * th * tw + txt_len
@@ -48,7 +49,8 @@ def test_sparse_diff_attn_matches_reference_modules(cm, cuda, monkeypatch, name,
     cfg["attn"].update(is_enabled=True, first_n_dense_layers=0, top_keys=tk / N, random_keys=0.0, local_voxels=local_voxels,
                        local_1d_window=0, full_step_every=10, full_step_schedule=None, recompute_mask=bool(compressed),
                        should_compress_indices=bool(compressed), counts_multiple_of=multiple_of,
-                       pad_qkv_before_kernel=bool(pad), torch_selection=torch_selection, random_columns=0.0)
+                       pad_qkv_before_kernel=bool(pad), torch_selection=torch_selection, random_columns=0.0,
+                       keep_indices_resident=resident)       # index lists kept in HBM between steps: same results
     if torch_selection:
         # the reference formulation draws its 1 % random columns with torch.randint: none, as in the fixture
         real = torch.randint
@@ -89,6 +91,7 @@ def test_sparse_diff_attn_matches_reference_modules(cm, cuda, monkeypatch, name,
     for s in (2, 3):
         _close(outs[s][:, :, ::ROW_STRIDE], want[s], 6e-3, what=f"{name} sparse step {s}")
     assert torch.equal(attn.storage.get_out_cache(), cache1), "sparse steps must leave the cache alone"
+    assert bool(attn._resident) == (resident and bool(compressed))
     assert counter.cur_inference_step == 4
 
 
