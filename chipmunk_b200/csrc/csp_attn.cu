@@ -12,13 +12,13 @@
 //     MMA warp (1 thread)  S = Q K^T   (tcgen05.mma SS, M=128 N<=128 K=128, fp32 in TMEM), twice:
 //                          query rows 0-127 ("block 0") and 128-191 ("block 1"),
 //                          O += P V    (tcgen05.mma TS: P read from TMEM, V as MN-major smem),
-//     softmax warps (4+4)  one thread per query row: TMEM -> regs, running max with lazy
-//                          rescale, exp2, row sum, P (bf16) written back over S in TMEM.  Block 1 is an M = 64
-//                          accumulator (row m on TMEM lane (m % 16) + 32 (m / 16)): 16 rows per lane quadrant, so
-//                          its four warps use lanes 0-15 each.  An M = 64 MMA takes as many cycles as an M = 128 one
-//                          but far less power (tests/probes/probe_mma_power.cu: under the 1 kW cap a pure MMA stream
-//                          clocks 1.81 GHz at M = 64, 1.57 GHz at M = 128 with 64 zero rows), and the kernel runs at the
-//                          cap: -3.3 % at the 720p shape against an M = 128 block 1 with two softmax warps,
+//     softmax warps (4+4)  TMEM -> regs, running max with lazy rescale, exp2, row sum, P (bf16) written back over S.
+//                          Block 0 (M = 128): one thread per query row, one warp per TMEM lane quadrant.  Block 1 is
+//                          an M = 64 accumulator (row m on lane (m % 16) + 32 (m / 16): 16 rows per quadrant), one
+//                          warp per quadrant with FOUR threads per row (16-lane TMEM shapes, softmax_step16): every
+//                          lane works.  An M = 64 MMA takes as many cycles as an M = 128 one but far less power
+//                          (tests/probes/probe_mma_power.cu: under the 1 kW cap a pure MMA stream clocks 1.81 GHz at
+//                          M = 64, 1.57 GHz at M = 128 with 64 zero rows), and the kernel runs at the cap,
 //     epilogue             (same threads) O / l * o_scale -> bf16 (+ the cached tile, read from shared memory) into a
 //                          128B-swizzled staging tile that the TMA thread stores (csp_128_attn, csp_attn_add) or
 //                          reduce-adds at the L2 (csp_attn, like the reference's TMA store_add, csp_attn.cu:300).
@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "../../include/chipmunk_b200.h"
 #include "common.cuh"
@@ -40,9 +41,7 @@
 #include "tma.cuh"
 
 #ifndef CM_ATTN_REG_SOFTMAX
-#define CM_ATTN_REG_SOFTMAX 208
-#define CM_ATTN_REG_MMA 32
-#define CM_ATTN_REG_PROD 64
+#define CM_ATTN_REG_SOFTMAX 208      // one thread per row: a 128-column score row per thread
 #endif
 
 namespace cm {
@@ -57,15 +56,20 @@ struct GEO {
     static constexpr int Q_BYTES = 2 * Q_HALF_BYTES;             // 48 KB
     static constexpr int STAGE_BYTES = Q_BYTES;                  // 48 KB: the cached output tile in, the output tile out (TMA both ways)
     static constexpr int SMEM_BYTES = Q_BYTES + STAGE_BYTES + NSLOT * SLOT_BYTES + 1024 /*align slack*/;
-    // warps 0-3 softmax blk0 | 4-7 softmax blk1 (16 rows each) | 8 MMA, 9 TMA (Q tile, cached tile, output tile), 10-11 idle |
-    // 12-15 K/V gather producers
+    // warps 0-3 softmax blk0 (rows 32 w + lane) | 4-7 softmax blk1 (rows 128 + 16 (w&3) + 0..15, four threads per row) |
+    // 8 MMA, 9 TMA (Q tile, cached tile, output tile), 10-11 idle | 12-15 K/V gather producers
     static constexpr int NUM_THREADS = 512;
     static constexpr int WARP_MMA = 8;
     static constexpr int WARP_TMA = 9;
     static constexpr int NUM_SOFTMAX_WARPS = 8;
-    static constexpr int REG_SOFTMAX = CM_ATTN_REG_SOFTMAX;      // setmaxnreg budgets per warpgroup: 64 K registers per SM
-    static constexpr int REG_MMA = CM_ATTN_REG_MMA;
-    static constexpr int REG_OTHER = CM_ATTN_REG_PROD;
+    // setmaxnreg budgets per warpgroup (softmax block 0 | softmax block 1 | MMA, TMA | producers); their sum must not exceed the
+    // launch allocation (512 x 128): a larger sum can never be granted and the kernel hangs in setmaxnreg.inc.
+    // QUAD = block 1 with four threads per row (two 32-column pieces per thread) leaves room for the other roles.
+    static constexpr int REG_SOFTMAX = CM_ATTN_REG_SOFTMAX;
+    template <bool QUAD> static constexpr int reg_softmax1() { return QUAD ? 160 : 208; }
+    template <bool QUAD> static constexpr int reg_mma() { return QUAD ? 64 : 32; }
+    template <bool QUAD> static constexpr int reg_prod() { return QUAD ? 80 : 64; }
+    static_assert(128 * (REG_SOFTMAX + 160 + 64 + 80) <= 65536 && 128 * (REG_SOFTMAX + 208 + 32 + 64) <= 65536, "setmaxnreg budgets exceed the register file");
 };
 constexpr int WARP_PROD0 = 12;
 constexpr int INACTIVE_ROW = 1 << 28;          // r_in_tile of the lanes 16-31 of a block-1 softmax warp: beyond every Nq
@@ -118,6 +122,10 @@ __device__ __forceinline__ int tile_count(const Params& P, int tile) {
 }
 
 // ------------------------------------------------------------------------------------------
+// QUAD: block 1's softmax runs with four threads per row, every lane busy (softmax_step16) -- the lower-power form, faster
+// on long key lists under the power cap (-2.2 % at the 720p shape); with one thread per row on lanes 0-15 the kernel is smaller
+// and has the lower per-tile cost (-2.9 % at FLUX sizes, 7 steps per tile).  Same TMEM layout: the MMA side is identical.
+template <bool QUAD>
 __global__ void __launch_bounds__(GEO::NUM_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_o, const Params P) {
     constexpr int QROWS = GEO::QROWS, Q_HALF_BYTES = GEO::Q_HALF_BYTES, Q_BYTES = GEO::Q_BYTES, WARP_MMA = GEO::WARP_MMA;
@@ -137,7 +145,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
         mbar_init(&bar.q_empty, 1);
         for (int i = 0; i < NSLOT; i++) { mbar_init(&bar.kv_full[i], NUM_PROD); mbar_init(&bar.kv_empty[i], 1); }
         mbar_init(&bar.s_full[0], 1);  mbar_init(&bar.s_full[1], 1);
-        mbar_init(&bar.p_full[0], 128); mbar_init(&bar.p_full[1], QROWS - 128);
+        mbar_init(&bar.p_full[0], 128); mbar_init(&bar.p_full[1], 128);     // every thread of a block's four softmax warps
         mbar_init(&bar.o_full[0], 1);  mbar_init(&bar.o_full[1], 1);
         fence_mbar_init();
     }
@@ -149,7 +157,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
 
     // =========================================================================== producers
     if (warp >= WARP_PROD0 && warp < WARP_PROD0 + 4) {
-        setmaxnreg_dec<GEO::REG_OTHER>();
+        setmaxnreg_dec<GEO::reg_prod<QUAD>()>();
         const int pt = tid - WARP_PROD0 * 32;       // 0..127
         const int chunk = pt & 15;                  // 16-byte chunk of the 256-byte row
         const int rsub = pt >> 4;                   // 0..7
@@ -210,7 +218,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     }
     // =========================================================================== MMA issuer
     else if (warp == WARP_MMA) {
-        setmaxnreg_dec<GEO::REG_MMA>();
+        setmaxnreg_dec<GEO::reg_mma<QUAD>()>();
         uint32_t job = 0, it = 0, sc0 = 0, sc1 = 0;   // slot jobs, tiles, S/P step counters per block
         const uint32_t idesc_pv0 = umma_idesc_bf16(128, D, 0, 1), idesc_pv1 = umma_idesc_bf16(64, D, 0, 1);
         const uint64_t desc_q = umma_smem_desc(sQ, 16, 1024);                    // K-major A: Q rows
@@ -305,15 +313,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     }
     // =========================================================================== softmax + epilogue
     else if (warp < GEO::NUM_SOFTMAX_WARPS) {
-        setmaxnreg_inc<GEO::REG_SOFTMAX>();
-        const int blk = warp >> 2;                         // 0: rows 0-127 (M = 128), 1: rows 128-191 (M = 64)
-        // block 1: row m of the M = 64 accumulator sits on TMEM lane (m % 16) + 32 (m / 16): lanes 0-15 of every quadrant;
-        // lanes 16-31 of its warps only take part in the warp-wide TMEM instructions
-        const bool active = blk == 0 || lane < 16;
-        const int r_in_tile = blk == 0 ? (warp & 3) * 32 + lane : (active ? 128 + (warp & 3) * 16 + lane : INACTIVE_ROW);
-        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      // the role body is instantiated once per block (separate code, separate register budgets)
+      auto softmax_role = [&](auto BLK) {
+        // 0: rows 0-127 (M = 128), 1: rows 128-191 (M = 64); BLKC < 0: one body for both blocks (the !QUAD kernel, whose two
+        // blocks run the same code: a smaller kernel)
+        constexpr int BLKC = decltype(BLK)::value;
+        const int blk = BLKC < 0 ? (warp >> 2) : BLKC;
+        const int q4 = warp & 3;
+        const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
         const uint32_t tS = tm + (blk ? TM_S1 : TM_S0) + lane_off;
         const uint32_t tO = tm + (blk ? TM_O1 : TM_O0) + lane_off;
+        // block 1, softmax: lanes 0-15 of the quadrant through the 16-lane shapes, four threads per row (thread t: rows
+        // t/4 and 8 + t/4).  Epilogue of both blocks: 32x32b, thread i on lane i -- block 1's rows sit on lanes 0-15.
+        const int c4 = lane & 3;
+        const bool active = blk == 0 || lane < 16;
+        const int ri = lane & 15;
+        const int r_in_tile = blk == 0 ? q4 * 32 + lane : (active ? 128 + q4 * 16 + ri : INACTIVE_ROW);
         uint32_t sc = 0, oc = 0;
         uint32_t ti = 0;                                   // tiles of this CTA so far (phases of c_full / st_full / st_free)
         const uint32_t sw = (uint32_t)(r_in_tile & 7);
@@ -355,20 +370,37 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
                 continue;
             }
             const int nk = (count + KT - 1) / KT;
-            float m_ref = -INFINITY;       // reference max, raw score units
-            float l_sum = 0.f;
+            constexpr bool quad = QUAD && BLKC == 1;
+            float m_ref = -INFINITY, l_sum = 0.f;          // one thread per row: reference max (raw score units) and row sum
+            float m_ref2[2] = {-INFINITY, -INFINITY};      // four threads per row: reference maxima of the thread's two rows,
+            float l_part[2] = {0.f, 0.f};                  //          this thread's share of their row sums
 
             for (int kk = 0; kk < nk; kk++) {
                 const int valid = min(KT, count - kk * KT);
                 mbar_wait(&bar.s_full[blk], sc & 1); sc++;
                 tc_fence_after_sync();
-                if (CM_DBG(P, 4)) { l_sum = 1.f; }
-                else if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum, active);
-                else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum, active);
-                else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum, active);
+                if (CM_DBG(P, 4)) { l_sum = l_part[0] = l_part[1] = 1.f; }
+                else if constexpr (!quad) {
+                    if (valid == KT) softmax_step<false>(tS, tO, KT, kk, m_ref, l_sum, active);
+                    else if (valid <= 32) softmax_step_narrow(tS, tO, valid, kk, m_ref, l_sum, active);
+                    else softmax_step<true>(tS, tO, valid, kk, m_ref, l_sum, active);
+                } else {
+                    if (valid == KT) softmax_step16<false>(tS, tO, KT, kk, m_ref2, l_part, c4);
+                    else if (valid <= 32) softmax_step16_narrow(tS, tO, valid, kk, m_ref2, l_part, c4);
+                    else softmax_step16<true>(tS, tO, valid, kk, m_ref2, l_part, c4);
+                }
                 tmem_st_wait();
                 tc_fence_before_sync();
-                if (active) mbar_arrive(&bar.p_full[blk]);
+                mbar_arrive(&bar.p_full[blk]);
+            }
+            // block 1 row sums: the four threads of a row add up their shares; the epilogue thread of row ri (one per row)
+            // fetches the sum from the row's group (rows 0-7 of the window are the groups' "A" rows, 8-15 their "B" rows)
+            if constexpr (quad) {
+                float la = l_part[0], lb = l_part[1];
+                la += __shfl_xor_sync(0xffffffffu, la, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 1);
+                la += __shfl_xor_sync(0xffffffffu, la, 2); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+                const float ga = __shfl_sync(0xffffffffu, la, 4 * (ri & 7)), gb = __shfl_sync(0xffffffffu, lb, 4 * (ri & 7));
+                l_sum = (ri & 8) ? gb : ga;
             }
             // ---- epilogue: O / l * scale (+ cached o) -> bf16
             if (P.stage) {
@@ -485,10 +517,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
             }
             tc_fence_before_sync();
         }
+      };
+      if constexpr (!QUAD) { setmaxnreg_inc<GEO::REG_SOFTMAX>(); softmax_role(std::integral_constant<int, -1>{}); }
+      else if (warp < 4) { setmaxnreg_inc<GEO::REG_SOFTMAX>(); softmax_role(std::integral_constant<int, 0>{}); }
+      else { setmaxnreg_inc<GEO::reg_softmax1<QUAD>()>(); softmax_role(std::integral_constant<int, 1>{}); }
     }
     else {
         // =========================================================================== TMA thread (warp 9); warps 10-11 idle
-        setmaxnreg_dec<GEO::REG_MMA>();            // warpgroup-wide: warps 8-11
+        setmaxnreg_dec<GEO::reg_mma<QUAD>()>();            // warpgroup-wide: warps 8-11
         if (warp == GEO::WARP_TMA && lane == 0) {
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_o);
             uint32_t qn = 0;                        // Q tiles loaded so far
@@ -552,8 +588,11 @@ using namespace cm;
 using namespace cm::attn;
 
 static int launch_attn(Params& P, cudaStream_t stream) {
-    static unsigned long long configured = 0;
-    int rc = opt_in_dynamic_smem(configured, reinterpret_cast<const void*>(attn_kernel), GEO::SMEM_BYTES);
+    // long sequences (the video shapes) take the four-threads-per-row form of block 1, short ones the smaller kernel
+    const bool quad = P.Nk >= 16384;
+    static unsigned long long configured[2] = {0, 0};
+    int rc = quad ? opt_in_dynamic_smem(configured[1], reinterpret_cast<const void*>(attn_kernel<true>), GEO::SMEM_BYTES)
+                  : opt_in_dynamic_smem(configured[0], reinterpret_cast<const void*>(attn_kernel<false>), GEO::SMEM_BYTES);
     if (rc) return rc;
     // tensor maps (cached per argument set): Q tile in, cached tile in, output tile out; boxes of 192 rows x 64 columns
     CUtensorMap mq, mc, mo;
@@ -563,7 +602,8 @@ static int launch_attn(Params& P, cudaStream_t stream) {
     if (rc) return rc;
     if (!P.cache) { mc = mo; for (int i = 0; i < 3; i++) P.pos[1][i] = P.pos[2][i]; }
     int grid = P.num_tiles < sm_count() ? P.num_tiles : sm_count();
-    attn_kernel<<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(mq, mc, mo, P);
+    if (quad) attn_kernel<true><<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(mq, mc, mo, P);
+    else attn_kernel<false><<<grid, GEO::NUM_THREADS, GEO::SMEM_BYTES, stream>>>(mq, mc, mo, P);
     return (int)cudaGetLastError();
 }
 
