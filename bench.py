@@ -288,7 +288,7 @@ def run_ours(args):
                              "smaller: a head's K/V (61 MB) stays in the 126 MB L2 under head-major tile order, so the gather is served by L2 "
                              "and the kernel is bound by its S -> softmax -> P.V chain (tensor pipe 63 % active) and by the 1 kW power "
                              "cap (it runs at ~1.6 of 1.965 GHz: profiles/r02_probe_mma_power.txt), not by HBM",
-                     "kernel": "attn::attn_kernel<false> (csp_attn_add)" + (" + fused multicast gather of O" if use_fused else (" + ncclAllGather" if world > 1 else "")),
+                     "kernel": "attn::attn_kernel<QUAD=true> (csp_attn_add)" + (" + fused multicast gather of O" if use_fused else (" + ncclAllGather" if world > 1 else "")),
                      "launch_us": round(t_attn * 1e3, 1), "algorithmic_bytes_per_launch": attn_alg_bytes(hl, n, count),
                      "tensor_tflops": round(4.0 * QG * count * D * hl * G / (t_attn * 1e-3) / 1e12, 1),
                      "tensor_frac_of_burst_peak": round(4.0 * QG * count * D * hl * G / (t_attn * 1e-3) / 1e12 / tf_burst, 4)})
