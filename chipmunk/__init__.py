@@ -11,18 +11,19 @@ import types
 
 import chipmunk_b200 as _impl
 from chipmunk_b200 import modules, ops, util  # noqa: F401
-from chipmunk_b200.modules import SparseDiffAttn, SparseDiffMlp  # noqa: F401
+from chipmunk_b200.modules import SparseDiffAttn, SparseDiffMlp, quantize_fp8  # noqa: F401
 from chipmunk_b200.util import GLOBAL_CONFIG, LayerCounter  # noqa: F401
 
-_alias = {
-    "chipmunk.ops": ops, "chipmunk.modules": modules, "chipmunk.util": util,
-    "chipmunk.ops.attn": _impl.ops.attn, "chipmunk.ops.mlp": _impl.ops.mlp,
-    "chipmunk.ops.indexed_io": _impl.ops.indexed_io, "chipmunk.ops.bitpack": _impl.ops.bitpack,
-    "chipmunk.ops.patch": _impl.ops.patch, "chipmunk.ops.voxel": _impl.ops.voxel,
-    "chipmunk.modules.attn": _impl.modules.attn, "chipmunk.modules.mlp": _impl.modules.mlp,
-    "chipmunk.util.config": _impl.util.config, "chipmunk.util.layer_counter": _impl.util.layer_counter,
-    "chipmunk.util.storage": _impl.util.storage,
-}
+# submodules are taken from sys.modules, not as attributes: `chipmunk_b200.ops.mlp` the ATTRIBUTE is the run_e2e function
+# (`from .mlp import run_e2e as mlp`, as in the reference's ops/__init__.py), the module is sys.modules[...]
+_SUBMODULES = (
+    "ops", "modules", "util",
+    "ops.attn", "ops.mlp", "ops.indexed_io", "ops.bitpack", "ops.patch", "ops.voxel",
+    "modules.attn", "modules.mlp",
+    "util.config", "util.layer_counter", "util.step_cache",
+    "util.storage", "util.storage.offloaded_tensor", "util.storage.layer_storage",
+)
+_alias = {f"chipmunk.{_n}": sys.modules[f"chipmunk_b200.{_n}"] for _n in _SUBMODULES}
 for _name, _mod in _alias.items():
     sys.modules.setdefault(_name, _mod)
 

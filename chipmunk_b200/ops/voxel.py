@@ -66,6 +66,55 @@ def masktoinds(mask: torch.Tensor, multiple=None):
     return inds.contiguous().to(torch.int32), counts.contiguous()
 
 
+def offsets(base_coord: int, full_size: int, offset_range: int):
+    """The 2*offset_range+1 relative positions a coordinate looks at along one axis: offset_range to either side, and
+    what does not fit on one side is made up for on the other (reference voxel.py:101-113, which only ever extends ONE
+    side: the left one is checked first)."""
+    left = min(offset_range, base_coord)
+    right = min(offset_range, full_size - 1 - base_coord)
+    if left < offset_range:
+        right += offset_range - left
+    elif right < offset_range:
+        left += offset_range - right
+    return list(range(-left, right + 1))
+
+
+def get_local_voxel_indices(full_shape, local_shape) -> torch.Tensor:
+    """[t*h*w, (lt+1)*(lh+1)*(lw+1)] int64 (CPU): for every voxel the flat indices of its local box, entry
+    (ic, jc, kc) of the box at column ic*(lh+1)*(lw+1) + jc*(lw+1) + kc; the box has 2*(l//2)+1 entries per axis, so for
+    odd extents the remaining columns keep their initial 0 (reference voxel.py:115-158, a six-deep Python loop; here
+    three per-axis tables combined by broadcasting)."""
+    t, h, w = full_shape
+    lt, lh, lw = local_shape
+    width = (lt + 1) * (lh + 1) * (lw + 1)
+    inds = torch.zeros(t * h * w, width, dtype=torch.int64)
+    if lt == 0 or lh == 0 or lw == 0:
+        return inds
+
+    def axis_table(n, l):
+        return torch.tensor([[b + o for o in offsets(b, n, l // 2)] for b in range(n)], dtype=torch.int64)   # [n, 2*(l//2)+1]
+
+    at, ah, aw = axis_table(t, lt), axis_table(h, lh), axis_table(w, lw)
+    nt, nh, nw = at.shape[1], ah.shape[1], aw.shape[1]
+    flat = (at[:, None, None, :, None, None] * (h * w) + ah[None, :, None, None, :, None] * w
+            + aw[None, None, :, None, None, :]).reshape(t * h * w, nt, nh, nw)
+    slot = (torch.arange(nt)[:, None, None] * ((lh + 1) * (lw + 1)) + torch.arange(nh)[None, :, None] * (lw + 1)
+            + torch.arange(nw)[None, None, :]).reshape(-1)
+    inds[:, slot] = flat.reshape(t * h * w, -1)
+    return inds
+
+
+def merge_indices(a: torch.Tensor, b: torch.Tensor, full_shape):
+    """Union of two index lists per row as (inds, counts) of the merged mask (reference voxel.py:182-204).
+    `full_shape` is the mask's shape [..., m, n] (a shape, or a tensor of that shape)."""
+    shape = tuple(full_shape.shape) if isinstance(full_shape, torch.Tensor) else tuple(full_shape)
+    assert a.shape[:-1] == b.shape[:-1] == shape[:-1], "a, b and full_shape must agree in every dimension but the last"
+    mask = torch.zeros(shape, device=a.device, dtype=torch.bool)
+    mask.scatter_(-1, a.long(), True)
+    mask.scatter_(-1, b.long(), True)
+    return masktoinds(mask)
+
+
 def _axis_window(n: int, reach: int, device) -> torch.Tensor:
     """[n, n] bool: window[i, j] = j is one of the 2*reach+1 positions around i, shifted inward at the
     borders so that every position sees exactly 2*reach+1 neighbours (reference `offsets`, voxel.py:101-113)."""

@@ -5,7 +5,7 @@ B200 difference: `offloading.global_disable_offloading` defaults to True.  The r
 each layer's caches to pinned host memory because an 80 GB H100 cannot hold them (731 MB per
 layer x 60 layers at HunyuanVideo 720p); 180 GB of HBM3e can, so caches stay resident unless a
 config file turns offloading back on -- and then `offloading.backing: peer` parks them in a neighbour GPU's HBM over
-NVLink instead of in host memory (util/storage.py).
+NVLink instead of in host memory (util/storage/).
 """
 from __future__ import annotations
 

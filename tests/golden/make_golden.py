@@ -92,6 +92,22 @@ def main():
         cases[f"lm_args{i}"] = np.array(list(vid) + [txt] + list(local))
         cases[f"lm_mask{i}"] = mask.numpy(); cases[f"lm_counts{i}"] = counts.numpy()
     np.savez_compressed(os.path.join(HERE, "reorder.npz"), **cases)
+    # ---- the helpers under the static local masks: per-axis offsets and the local-box index table (ops/voxel.py:101-158)
+    cases = {}
+    grid = [(b, n, r) for n in (1, 2, 3, 5, 8) for r in (0, 1, 2, 3) for b in range(n) if not (n == 1 and r > 0)]
+    offs = []
+    for b, n, r in grid:
+        try:
+            offs.append((b, n, r, ref_voxel.offsets(b, n, r)))
+        except IndexError:            # the reference indexes an empty list when neither side has room (n == 1 handled above)
+            pass
+    cases["offsets_args"] = np.array([o[:3] for o in offs], dtype=np.int64)
+    cases["offsets_flat"] = np.array([v for o in offs for v in o[3]], dtype=np.int64)
+    cases["offsets_len"] = np.array([len(o[3]) for o in offs], dtype=np.int64)
+    for i, (full, local) in enumerate([((3, 4, 5), (2, 2, 2)), ((4, 4, 4), (3, 3, 3)), ((2, 3, 6), (2, 0, 2)), ((5, 3, 4), (4, 2, 2)), ((6, 6, 6), (1, 1, 1))]):
+        cases[f"lvi_args{i}"] = np.array(list(full) + list(local))
+        cases[f"lvi{i}"] = ref_voxel.get_local_voxel_indices(full, local).numpy()
+    np.savez_compressed(os.path.join(HERE, "voxel_indices.npz"), **cases)
     print("wrote", sorted(os.listdir(HERE)))
 
 
