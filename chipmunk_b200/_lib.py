@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CHIPMUNK_B200_LIB: development override for same-box A/B timing of two builds (never a fallback: it must exist)
 LIB_PATH = os.environ.get("CHIPMUNK_B200_LIB") or os.path.join(_HERE, "libchipmunk_b200.so")
 
+ABI_VERSION = 2          # must equal CM_ABI_VERSION of include/chipmunk_b200.h (checked at load time and by the CPU tests)
 CM_BF16, CM_F16, CM_F32 = 0, 1, 2
 _DTYPE_TAG = {torch.bfloat16: CM_BF16, torch.float16: CM_F16, torch.float32: CM_F32}
 
@@ -52,6 +53,10 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError here = header and library disagree
         fn.argtypes = args
         fn.restype = res
+    got = lib.cm_abi_version()
+    if got != ABI_VERSION:     # a stale build: same symbol names, possibly different argument lists
+        raise ImportError(f"{LIB_PATH} reports ABI version {got}, this package binds version {ABI_VERSION}: "
+                          "rebuild it with `python chipmunk_b200/build.py --force`")
     return lib
 
 

@@ -25,6 +25,10 @@ def test_library_exports_every_declared_symbol(cm):
         assert hasattr(lib, s), f"{s} declared in include/chipmunk_b200.h but not exported"
     assert set(syms) == set(cm._lib.EXPORTS)
     assert lib.cm_abi_version() == 2      # round 2: + cm_select_columns, cm_dense_attn_strided
+    import re
+    from chipmunk_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "chipmunk_b200.h")).read()
+    assert int(re.search(r"#define\s+CM_ABI_VERSION\s+(\d+)", hdr).group(1)) == _lib.ABI_VERSION == lib.cm_abi_version()
     lib.cm_strerror.restype = ctypes.c_char_p
     assert b"16-byte" in lib.cm_strerror(-2)
 
