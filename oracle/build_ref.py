@@ -58,12 +58,40 @@ def stage_triton(force: bool = False) -> str | None:
     return TRITON_OUT
 
 
+# The reference's Python host side of the path -- its op wrappers (padding / slicing around the kernels), its modules and its
+# util package -- is staged the same way into oracle/_ref/chipmunk_py/chipmunk/{ops,modules,util}: tests/test_ref_python_gpu.py
+# runs THAT code, unmodified, on top of this repo's `torch.ops.chipmunk.*` kernels (INTEGRATION.md option 2) and compares with the
+# golden vectors.  `triton/` and the compiled `cuda` module are not staged: the runner supplies empty modules for them.
+PY_PACKAGES = ("ops", "modules", "util")
+PY_OUT = os.path.join(OUT, "chipmunk_py")
+
+
+def stage_python(force: bool = False) -> str | None:
+    src_root = os.path.join(REF, "src", "chipmunk")
+    if not all(os.path.isdir(os.path.join(src_root, p)) for p in PY_PACKAGES):
+        return PY_OUT if os.path.isdir(PY_OUT) else None
+    for pkg in PY_PACKAGES:
+        for d, _, files in os.walk(os.path.join(src_root, pkg)):
+            rel = os.path.relpath(d, src_root)
+            if "__pycache__" in rel:
+                continue
+            os.makedirs(os.path.join(PY_OUT, "chipmunk", rel), exist_ok=True)
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                s, dst = os.path.join(d, f), os.path.join(PY_OUT, "chipmunk", rel, f)
+                if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(s):
+                    shutil.copyfile(s, dst)
+    return PY_OUT
+
+
 def available() -> bool:
     return all(os.path.exists(s) for s in SOURCES)
 
 
 def build(force: bool = False) -> str | None:
     stage_triton(force)
+    stage_python(force)
     if os.path.exists(LIB) and not force:
         return LIB
     if not available():
