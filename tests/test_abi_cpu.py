@@ -178,3 +178,49 @@ def test_step_cache_glue(cm):
     with pytest.raises(RuntimeError):
         sc.try_skip(7, counter)
     reset_to_defaults()
+
+
+def test_operators_trace_under_fake_tensors(cm):
+    """the operators must be callable inside torch.compile'd blocks (the example models compile their
+    transformer blocks).  Every operator has a fake (meta) kernel with the shapes / dtypes the real one allocates, and a
+    sparse step traces to a graph that holds the `chipmunk::` nodes -- checked with fake CUDA tensors, no GPU needed."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.fx.experimental.proxy_tensor import make_fx
+
+    B, H, N = 1, 2, 500
+    G, padN = (N + 191) // 192, 576
+    with FakeTensorMode() as mode:
+        bf = dict(dtype=torch.bfloat16, device="cuda")
+        q = torch.empty(B, H, N, 128, **bf)
+        idx = torch.empty(B, H, G, padN, dtype=torch.int32, device="cuda")
+        cnt = torch.empty(B, H, G, dtype=torch.int32, device="cuda")
+        o = torch.ops.chipmunk.csp_128_attn(q, q, q, idx, cnt)
+        assert o.shape == q.shape and o.dtype == torch.bfloat16 and o.device.type == "cuda"
+        o, l = torch.ops.chipmunk.dense_attn(q, q, q)
+        assert o.shape == q.shape and l.shape == (B, H, N, 1) and l.dtype == torch.float32
+        p = torch.empty(B, H, N, 1, dtype=torch.float32, device="cuda")
+        o, cs, l = torch.ops.chipmunk.dense_colsum_attn(q, q, q, p)
+        assert cs.shape == (B, H, G, N) and cs.dtype == torch.bfloat16 and l.shape == (B, H, N, 1)
+        inds, counts = torch.ops.chipmunk.mask_to_indices(torch.empty(B, H, G, N, dtype=torch.bool, device="cuda"), 128, 192)
+        assert inds.shape == (B, H, G, padN) and counts.shape == (B, H, G) and inds.dtype == counts.dtype == torch.int32
+        # in-place operators return nothing
+        assert torch.ops.chipmunk.csp_attn(q, q, q, torch.empty_like(q), idx, cnt, 1) is None
+        M, K, F = 256, 128, 512
+        a, w1, c = torch.empty(M, K, **bf), torch.empty(F, K, **bf), torch.empty(M, F, **bf)
+        mi, mc = torch.empty(M // 128, F, dtype=torch.int32, device="cuda"), torch.empty(M // 128, dtype=torch.int32, device="cuda")
+        assert torch.ops.chipmunk.csp_mlp_mm1(a, w1, c, torch.empty(F, **bf), torch.empty(F, M, **bf), mi, mc) is None
+        assert torch.ops.chipmunk.csp_scatter_add(c[None], torch.empty(1, F, M, **bf), mi[None], mc[None], 6) is None
+        assert torch.ops.chipmunk.csp_mlp_mm2_and_scatter_add(c[None], torch.empty(1, F, M, **bf), mi[None], mc[None], c[None],
+                                                              torch.empty(1, F, K, **bf), torch.empty(1, M, K, **bf), 6, 0) is None
+        act = torch.empty(1, M // 128, F, **bf)
+        assert torch.ops.chipmunk.topk_indices(act, mi[None], mc[None], 0.7, 256, 0.0) is None
+        assert torch.ops.chipmunk.copy_indices(act, torch.empty_like(act), mi[None], mc[None]) is None
+
+        def sparse_step(q, k, v, cache, idx, cnt):
+            o = cache.clone()
+            torch.ops.chipmunk.csp_attn(q, k, v, o, idx, cnt, 1)
+            return o + torch.ops.chipmunk.csp_128_attn(q, k, v, idx, cnt)
+
+        gm = make_fx(sparse_step)(q, q, q, torch.empty_like(q), idx, cnt)
+    targets = [str(n.target) for n in gm.graph.nodes if n.op == "call_function"]
+    assert any("chipmunk.csp_attn" in t for t in targets) and any("chipmunk.csp_128_attn" in t for t in targets), targets
