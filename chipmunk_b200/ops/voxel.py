@@ -92,15 +92,25 @@ def get_local_voxel_indices(full_shape, local_shape) -> torch.Tensor:
         return inds
 
     def axis_table(n, l):
-        return torch.tensor([[b + o for o in offsets(b, n, l // 2)] for b in range(n)], dtype=torch.int64)   # [n, 2*(l//2)+1]
+        # [n, 2*(l//2)+1] absolute coordinates + which entries exist (a coordinate's list is shorter, and may leave the grid,
+        # where the axis is too short for the window: reproduced as the reference produces it)
+        width_ = 2 * (l // 2) + 1
+        rows = [[b + o for o in offsets(b, n, l // 2)] for b in range(n)]
+        tab = torch.tensor([r + [0] * (width_ - len(r)) for r in rows], dtype=torch.int64)
+        ok = torch.tensor([[True] * len(r) + [False] * (width_ - len(r)) for r in rows])
+        return tab, ok
 
-    at, ah, aw = axis_table(t, lt), axis_table(h, lh), axis_table(w, lw)
+    (at, vt_), (ah, vh_), (aw, vw_) = axis_table(t, lt), axis_table(h, lh), axis_table(w, lw)
     nt, nh, nw = at.shape[1], ah.shape[1], aw.shape[1]
-    flat = (at[:, None, None, :, None, None] * (h * w) + ah[None, :, None, None, :, None] * w
-            + aw[None, None, :, None, None, :]).reshape(t * h * w, nt, nh, nw)
+
+    def outer(x, y, z, op):
+        return op(op(x[:, None, None, :, None, None], y[None, :, None, None, :, None]), z[None, None, :, None, None, :])
+
+    flat = outer(at * (h * w), ah * w, aw, torch.add).reshape(t * h * w, -1)
+    valid = outer(vt_, vh_, vw_, torch.logical_and).reshape(t * h * w, -1)
     slot = (torch.arange(nt)[:, None, None] * ((lh + 1) * (lw + 1)) + torch.arange(nh)[None, :, None] * (lw + 1)
             + torch.arange(nw)[None, None, :]).reshape(-1)
-    inds[:, slot] = flat.reshape(t * h * w, -1)
+    inds[:, slot] = torch.where(valid, flat, torch.zeros_like(flat))
     return inds
 
 
@@ -164,7 +174,7 @@ def get_local_indices_with_text(vid_shape, txt_len, voxel_shape, local_shape, fu
     mask[:rows, :cols] |= local
     pad0, pad1 = n_groups - n_img, seq - cols
     if pad1 > 0 and full_tail_to_attn:
-        mask[:rows, cols:] = True
+        mask[:, cols:] = True        # every query group, the ragged-tail groups included (reference voxel.py:262-279)
     local_size = vsize * lt * lh * lw
     if local_size > 0 and pad0 > 0:
         mask[n_groups - pad0:, seq - local_size:] = True

@@ -1,0 +1,97 @@
+"""Token reorderings and static masks against the LIVE reference code over many shapes (authoring container only: the
+reference's src/chipmunk/ops/{patch,voxel}.py are imported by path from /root/reference, as tests/golden/make_golden.py does;
+elsewhere the committed fixtures of tests/test_oracle.py stand in).  The reference builds these transforms from chains of
+einops rearranges and Python loops, this repo from one cached permutation / vectorised windows: they must agree exactly,
+ragged tails, odd local extents and every flag of `get_local_indices_with_text` included."""
+import importlib.util
+import itertools
+import os
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference/src/chipmunk/ops"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference is only mounted in the authoring container")
+
+
+@pytest.fixture(scope="module")
+def ref(cm):
+    from chipmunk_b200.util.config import reset_to_defaults
+    reset_to_defaults()
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)          # `from chipmunk.util import GLOBAL_CONFIG` in the reference's patch.py -> the alias package
+    mods = {}
+    for name in ("patch", "voxel"):
+        spec = importlib.util.spec_from_file_location(f"_ref_live_{name}", os.path.join(REF, f"{name}.py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    return mods
+
+
+@pytest.mark.parametrize("h,w", [(8, 8), (16, 24), (24, 16), (64, 64), (40, 72), (8, 128)])
+def test_patchify_matches_the_reference(cm, ref, h, w):
+    from chipmunk_b200.ops import patch
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x = torch.randn(3, h, w, generator=g)
+    want = ref["patch"].patchify(x)
+    got = patch.patchify(x)
+    assert torch.equal(got, want)
+    assert torch.equal(patch.unpatchify(got, x.shape), ref["patch"].unpatchify(want, x.shape))
+    assert torch.equal(patch.unpatchify(got, x.shape), x)
+    pe = torch.randn(1, 2, 7 + h * w, 4, 2, 2, generator=g)
+    assert torch.equal(patch.patchify_rope((1, h * w, 8), pe.clone(), w, h), ref["patch"].patchify_rope((1, h * w, 8), pe.clone(), w, h))
+
+
+@pytest.mark.parametrize("thw,vox", [((8, 12, 16), (4, 6, 8)), ((9, 13, 17), (4, 6, 8)), ((5, 4, 6), (4, 4, 4)), ((4, 6, 8), (4, 6, 8)),
+                                     ((3, 5, 7), (4, 6, 8)), ((12, 7, 9), (2, 3, 4)), ((9, 34, 60), (4, 6, 8)), ((1, 6, 8), (1, 6, 8))])
+def test_voxel_chunking_matches_the_reference(cm, ref, thw, vox):
+    from chipmunk_b200.ops import voxel
+    g = torch.Generator().manual_seed(sum(thw))
+    x = torch.randn(2, 2, *thw, 3, generator=g)
+    if any(a < b for a, b in zip(thw, vox)):
+        # no whole voxel fits: the reference cannot express it (einops on an empty main block); ours must still round-trip
+        y = voxel.voxel_chunk_no_padding(x, vox)
+        assert torch.equal(voxel.reverse_voxel_chunk_no_padding(y, x.shape, vox), x)
+        return
+    want = ref["voxel"].voxel_chunk_no_padding(x, voxel_shape=vox)
+    got = voxel.voxel_chunk_no_padding(x, vox)
+    assert torch.equal(got, want)
+    assert torch.equal(voxel.reverse_voxel_chunk_no_padding(got, x.shape, vox), x)
+    assert torch.equal(ref["voxel"].reverse_voxel_chunk_no_padding(want, x.shape, voxel_shape=vox), x)
+
+
+@pytest.mark.parametrize("vid,txt,local", [((12, 18, 24), 40, (2, 2, 2)), ((8, 12, 16), 0, (1, 1, 1)), ((13, 19, 25), 70, (2, 2, 2)),
+                                           ((16, 24, 32), 256, (3, 3, 3)), ((8, 24, 32), 100, (0, 0, 0)), ((12, 12, 24), 33, (2, 1, 3)),
+                                           ((9, 34, 60), 256, (1, 1, 1))])
+@pytest.mark.parametrize("tail_from,tail_to", [(False, False), (True, False), (False, True), (True, True)])
+def test_static_local_masks_match_the_reference(cm, ref, vid, txt, local, tail_from, tail_to):
+    from chipmunk_b200.ops import voxel
+    kw = dict(full_tail_from_attn=tail_from, full_tail_to_attn=tail_to, rk=0, kv_tile_size=128, device=torch.device("cpu"))
+    want_mask, want_inds, want_counts = ref["voxel"].get_local_indices_with_text(vid, txt, (4, 6, 8), local, **kw)
+    mask, inds, counts = voxel.get_local_indices_with_text(vid, txt, (4, 6, 8), local, **kw)
+    assert torch.equal(mask, want_mask)
+    assert torch.equal(counts, want_counts)
+    nnz = mask.sum(-1)
+    for r in range(mask.shape[0]):            # the reference's argsort is not stable: compare the index SETS
+        n = int(nnz[r])
+        assert torch.equal(inds[r, :n].sort().values, want_inds[r, :n].sort().values)
+
+
+def test_local_voxel_tables_match_the_reference(cm, ref):
+    from chipmunk_b200.ops import voxel
+    for full, local in itertools.product([(2, 3, 4), (3, 3, 3), (4, 5, 2), (5, 6, 7)], [(1, 1, 1), (2, 2, 2), (3, 3, 3), (2, 1, 3), (4, 2, 2), (2, 0, 2)]):
+        if any(l // 2 > 0 and f == 1 for f, l in zip(full, local)):
+            continue
+        try:
+            want = ref["voxel"].get_local_voxel_indices(full, local)
+        except IndexError:
+            continue        # the reference's `offsets` indexes an empty list when an axis has no room on either side
+        assert torch.equal(voxel.get_local_voxel_indices(full, local), want), (full, local)
+        if int(want.max()) >= want.shape[0]:
+            continue        # an axis shorter than its window: the reference's table runs off the grid (its own scatter_ would raise)
+        # and the mask form used by get_local_indices_with_text scatters exactly these indices
+        m = torch.zeros(want.shape[0], want.shape[0], dtype=torch.bool)
+        m.scatter_(-1, want, True)
+        assert torch.equal(voxel.get_local_voxel_mask(full, local, torch.device("cpu")), m), (full, local)
