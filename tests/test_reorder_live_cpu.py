@@ -95,3 +95,44 @@ def test_local_voxel_tables_match_the_reference(cm, ref):
         m = torch.zeros(want.shape[0], want.shape[0], dtype=torch.bool)
         m.scatter_(-1, want, True)
         assert torch.equal(voxel.get_local_voxel_mask(full, local, torch.device("cpu")), m), (full, local)
+
+
+@pytest.mark.parametrize("seq,txt,lv,lw1d,top", [((8, 12, 16), 64, 1, 0.0, 0.05), ((8, 12, 16), 64, 0, 0.1, 0.05), ((12, 18, 24), 40, 2, 0.05, 0.1),
+                                                 ((9, 13, 17), 70, 1, 0.3, 0.3), ((16, 24, 32), 256, 3, 0.0, 0.6), ((4, 6, 8), 5, 0, 0.0, 0.05),
+                                                 ((16, 24, 32), 100, 1, 1.0, 0.01)])
+def test_initialize_static_mask_matches_the_reference_module(cm, ref, monkeypatch, seq, txt, lv, lw1d, top):
+    """`SparseDiffAttn.initialize_static_mask` (3-D local voxels + the 1-D window + which query groups stay sparse) against the
+    reference's module code (src/chipmunk/modules/attn.py:23-73), which loops over the query groups in Python."""
+    import numpy as np
+    import chipmunk  # noqa: F401  the alias package: `chipmunk.util`, `chipmunk.ops` of the reference module resolve to this repo ...
+    import chipmunk_b200.modules.attn as OurA
+    from chipmunk_b200.util.config import GLOBAL_CONFIG, reset_to_defaults
+    from chipmunk_b200.util.layer_counter import LayerCounter
+
+    reset_to_defaults()
+    GLOBAL_CONFIG["attn"].update(top_keys=top, random_keys=0.0, local_voxels=lv, local_1d_window=lw1d)
+    monkeypatch.setitem(sys.modules, "chipmunk.ops.voxel", ref["voxel"])        # ... except the voxel masks: the reference's own
+    spec = importlib.util.spec_from_file_location("_ref_live_modules_attn", "/root/reference/src/chipmunk/modules/attn.py")
+    RefA = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RefA)
+    H, dev = 2, torch.device("cpu")
+    RefA.SparseDiffAttn(0, LayerCounter(1, 1)).initialize_static_mask(seq, txt, H, dev)
+
+    def pack_rows_on_cpu(mask2d):          # ops.pack_rows_to_words is a CUDA kernel; same layout with numpy for this CPU test
+        R, n = mask2d.shape
+        W = (n + 31) // 32
+        padded = np.zeros((R, W * 32), dtype=np.uint8)
+        padded[:, :n] = mask2d.numpy()
+        return torch.from_numpy(np.packbits(padded, axis=1, bitorder="little").view(np.int32).reshape(R, W).copy())
+    monkeypatch.setattr(OurA.ops, "pack_rows_to_words", pack_rows_on_cpu)
+    for name in ("singleton_static_mask", "singleton_video_query_groups", "singleton_static_words", "singleton_group_flags"):
+        monkeypatch.setattr(OurA, name, None)
+    OurA.SparseDiffAttn(0, LayerCounter(1, 1)).initialize_static_mask(seq, txt, H, dev)
+    assert torch.equal(OurA.singleton_static_mask, RefA.singleton_static_mask)
+    assert torch.equal(OurA.singleton_video_query_groups, RefA.singleton_video_query_groups)
+    # the bit-packed copy handed to select_columns is that mask, and the group flags are that column
+    words = OurA.singleton_static_words.numpy().view(np.uint8)
+    bits = np.unpackbits(words, axis=1, bitorder="little")[:, : RefA.singleton_static_mask.shape[-1]].astype(bool)
+    assert np.array_equal(bits, RefA.singleton_static_mask[0, 0].numpy())
+    assert torch.equal(OurA.singleton_group_flags, RefA.singleton_video_query_groups[0, 0, :, 0])
+    reset_to_defaults()
