@@ -136,3 +136,35 @@ def test_initialize_static_mask_matches_the_reference_module(cm, ref, monkeypatc
     assert np.array_equal(bits, RefA.singleton_static_mask[0, 0].numpy())
     assert torch.equal(OurA.singleton_group_flags, RefA.singleton_video_query_groups[0, 0, :, 0])
     reset_to_defaults()
+
+
+def test_oracle_index_path_matches_the_reference_python_on_random_shapes(oracle, ref):
+    """The oracle's bit codec and mask -> indices (sets + padded counts) against the reference's own torch functions
+    (ops/bitpack.py run eagerly, ops/voxel.py:masktoinds) on 40 random shapes / densities / multiples -- the committed fixtures
+    of tests/test_oracle.py hold five."""
+    real_compile = torch.compile
+    torch.compile = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_live_bitpack", os.path.join(REF, "bitpack.py"))
+        bp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bp)
+    finally:
+        torch.compile = real_compile
+    g = torch.Generator().manual_seed(4242)
+    for i in range(40):
+        b, h, m = (int(torch.randint(1, 4, (1,), generator=g)) for _ in range(3))
+        n = int(torch.randint(1, 700, (1,), generator=g))
+        dens = float(torch.rand(1, generator=g)) ** 2
+        mult = (16, 112, 128, 192)[i % 4]
+        mask = torch.rand(b, h, m, n, generator=g) < dens
+        packed, shape = bp.bitpack(mask)
+        opacked, oshape = oracle.bitpack(mask)
+        assert torch.equal(opacked, packed) and tuple(oshape) == tuple(shape)
+        assert torch.equal(oracle.bitunpack(packed, shape), mask) and torch.equal(bp.bitunpack(packed, shape), mask)
+        want_inds, want_counts = ref["voxel"].masktoinds(mask, multiple=mult)
+        inds, counts = oracle.mask_to_indices(mask, mult, 192)
+        assert torch.equal(counts, want_counts), (i, n, mult)
+        nnz = mask.sum(-1)
+        flat_i, flat_w = inds.reshape(-1, inds.shape[-1]), want_inds.reshape(-1, n)
+        for r, c in enumerate(nnz.reshape(-1).tolist()):
+            assert torch.equal(flat_i[r, :c].sort().values, flat_w[r, :c].sort().values), (i, r)
