@@ -13,6 +13,10 @@ import chipmunk_b200 as _impl
 from chipmunk_b200 import modules, ops, util  # noqa: F401
 from chipmunk_b200.modules import SparseDiffAttn, SparseDiffMlp, quantize_fp8  # noqa: F401
 from chipmunk_b200.util import GLOBAL_CONFIG, LayerCounter  # noqa: F401
+# the reference's own voxel tests (src/chipmunk/tests/test_voxel.py:4-10, examples/hunyuan/.../test_chipmunk.py) import these
+# from the top level of the package
+from chipmunk_b200.ops.voxel import (get_local_indices_with_text, get_local_voxel_indices, masktoinds,  # noqa: F401
+                                     reverse_voxel_chunk_no_padding, voxel_chunk_no_padding)
 
 # submodules are taken from sys.modules, not as attributes: `chipmunk_b200.ops.mlp` the ATTRIBUTE is the run_e2e function
 # (`from .mlp import run_e2e as mlp`, as in the reference's ops/__init__.py), the module is sys.modules[...]

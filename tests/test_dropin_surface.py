@@ -113,3 +113,28 @@ def test_every_chipmunk_import_of_the_reference_examples_resolves():
     for s in missing:
         mod, names = s[5:].split(" import ")
         assert {n.strip() for n in names.split(",")} <= have.get(mod, set()), f"EXAMPLE_IMPORTS lacks: {s}"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/chipmunk/tests/test_voxel.py"),
+                    reason="the reference is only mounted in the authoring container")
+def test_the_references_own_voxel_tests_pass_against_this_package():
+    """src/chipmunk/tests/test_voxel.py, unmodified, with `chipmunk` = this repo's alias package: its assertions (voxel order of
+    the first chunks, round trips at toy and HunyuanVideo shapes incl. ragged tails) hold for the permutation-based
+    implementation, and its mask / index-table calls run."""
+    code = r'''
+import importlib.util, sys
+sys.path.insert(0, sys.argv[1])
+spec = importlib.util.spec_from_file_location("ref_test_voxel", "/root/reference/src/chipmunk/tests/test_voxel.py")
+mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+import chipmunk_b200.ops.voxel as ours
+assert mod.voxel_chunk_no_padding is ours.voxel_chunk_no_padding and mod.get_local_indices_with_text is ours.get_local_indices_with_text
+ran = 0
+for name in sorted(dir(mod)):
+    if name.startswith("test_") and callable(getattr(mod, name)):
+        getattr(mod, name)(); ran += 1
+print("RAN", ran)
+'''
+    r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, cwd="/tmp", timeout=900,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "RAN 6" in r.stdout, r.stdout[-500:]
